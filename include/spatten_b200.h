@@ -1,0 +1,109 @@
+/*
+ * spatten_b200 -- C ABI of the B200-native sparse-attention decode path.
+ *
+ * Drop-in boundary for mit-han-lab/spatten's `spatten_llm` hot path.  The reference has no FFI of
+ * its own (pure PyTorch), so every entry point below cites the reference *Python*
+ * interface it replaces; INTEGRATION.md shows the ctypes stub a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / CUDA types in any signature (`stream` is a cudaStream_t
+ *     passed as void*; NULL = legacy default stream).
+ *   - all data pointers are DEVICE pointers owned by the caller unless the name ends in `_host`.
+ *   - the library allocates nothing after the first call on a device (it caches device properties).
+ *   - every function returns SPATTEN_OK (0) or a negative SPATTEN_ERR_* code and never throws;
+ *     `spatten_last_error()` returns a thread-local human-readable message for the last failure.
+ *   - fp16 = IEEE binary16 (CUDA __half), row-major, innermost dimension contiguous.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns SPATTEN_ERR_CUDA.
+ */
+#ifndef SPATTEN_B200_H_
+#define SPATTEN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPATTEN_ABI_VERSION 1
+
+#define SPATTEN_OK 0
+#define SPATTEN_ERR_INVALID (-1)      /* bad argument (NULL pointer, shape, alignment) */
+#define SPATTEN_ERR_UNSUPPORTED (-2)  /* valid request the kernels do not implement (e.g. head_dim) */
+#define SPATTEN_ERR_CUDA (-3)         /* CUDA runtime error, message carries cudaGetErrorString */
+#define SPATTEN_ERR_WORKSPACE (-4)    /* workspace too small / not initialised */
+
+int spatten_abi_version(void);
+const char* spatten_last_error(void);
+/* SM count and compute capability of the current device. */
+int spatten_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * Decode attention: one new token per sequence against the (pruned) KV cache.
+ *
+ * Replaces the attention core of `llama_pos_shift_attention_forward` for q_len == 1
+ * (spatten_llm/pos_shift/modify_llama.py:86-144): RoPE(Q at position_ids) :92, KV append :95-100
+ * (keys cached UN-rotated), RoPE(K at cache-slot index) :103-104, Q.K^T/sqrt(D) :111, logits stash
+ * `self.attn_scores` :116-119, additive mask :127-132, fp32 softmax :135, P.V :138 -- in ONE kernel
+ * launch, without the O(S) cat / re-rotation / clone passes the reference pays every step.
+ *
+ * Numerics follow the reference op-for-op where it matters for the pruned index set: rotated keys
+ * and queries are rounded to fp16 after each elementwise op exactly as torch does (:27), the dot
+ * product accumulates in fp32 and is rounded to fp16, then divided by sqrt(D) (IEEE division) and
+ * rounded to fp16 again (:111-113); softmax runs in fp32 on those fp16 logits (:135).
+ * ---------------------------------------------------------------------------------------------- */
+/* Launch with programmatic dependent launch (PDL): the kernel lets its successor in the stream start
+ * early and itself waits (griddepcontrol.wait) for its predecessor before touching any argument. */
+#define SPATTEN_DECODE_PDL 1u
+/* With SPATTEN_DECODE_PDL: the caller guarantees that the cached rows [0, kv_len) of k_cache/v_cache and
+ * the `rope` table were NOT written by any kernel that can still be in flight when this one starts (true in
+ * a decoder: a layer's cache was last written one whole decode step earlier).  The kernel then streams the
+ * first K/V tiles into shared memory BEFORE waiting for its predecessor, hiding launch + HBM latency. */
+#define SPATTEN_DECODE_PDL_KV_STABLE 2u
+
+typedef struct SpattenDecodeArgs {
+  uint32_t struct_size;   /* = sizeof(SpattenDecodeArgs), ABI guard */
+  int32_t batch;          /* b */
+  int32_t num_heads;      /* H   (query heads) */
+  int32_t num_kv_heads;   /* H_kv (H % H_kv == 0; repeat_kv :108-109 is resolved by indexing) */
+  int32_t head_dim;       /* D: 64 or 128 */
+  int32_t kv_len;         /* tokens already in the cache (same for every sequence and head, as in the
+                             reference where the cache is one [b,H_kv,S,D] tensor) */
+  int32_t rope_len;       /* rows in `rope`; must be >= kv_len + 1 and > every q_pos */
+  int32_t append;         /* 1: write k_new/v_new into slot kv_len and attend over kv_len+1 tokens
+                             (reference behaviour); 0: attend over the kv_len cached tokens only */
+  uint32_t flags;         /* SPATTEN_DECODE_* bits below */
+
+  const void* q;          /* fp16 [b, H, D]      un-rotated query of the new token (after q_proj) */
+  const void* k_new;      /* fp16 [b, H_kv, D]   un-rotated key   (append == 1) */
+  const void* v_new;      /* fp16 [b, H_kv, D]   value            (append == 1) */
+  void* k_cache;          /* fp16 [b, H_kv, >=kv_len+append, D] un-rotated keys, strides below */
+  void* v_cache;          /* fp16 same layout */
+  int64_t cache_stride_b; /* elements between sequences  */
+  int64_t cache_stride_h; /* elements between kv heads (= capacity * D for a preallocated cache) */
+  const void* rope;       /* fp16 [rope_len, D]: row p = cos(p*theta_i) i<D/2 | sin(p*theta_i) i<D/2,
+                             i.e. the first halves of HF-4.33 LlamaRotaryEmbedding's cos/sin rows (:89) */
+  const int64_t* q_pos;   /* [b] position_ids of the query (:92); NULL = kv_len */
+  const void* mask;       /* optional fp16 additive mask [b, kv_len+append] (:127-132); NULL = none */
+  const uint8_t* head_mask; /* optional [H]; 0 = pruned head: no KV read, output row zeroed */
+
+  void* out;              /* fp16 [b, H, D] == attn_output[b, 1, H*D] before o_proj (:146-147) */
+  void* logits;           /* optional fp16 [b, H, logits_stride]: attn_scores[b,h,0,:] (:116-119) */
+  int64_t logits_stride;  /* elements between (b,h) rows of `logits` (>= kv_len+append) */
+  float* importance;      /* optional fp32 [b, H, importance_stride]: += softmax probability
+                             (cumulative token importance, README.md:21) */
+  int64_t importance_stride;
+  float* head_importance; /* optional fp32 [H]: += sum_d |out[b,h,d]| (head importance) */
+
+  void* workspace;        /* >= spatten_decode_workspace_bytes(...) bytes, zero-filled ONCE by the caller
+                             before first use (the kernel restores its counters to zero) */
+  size_t workspace_bytes;
+} SpattenDecodeArgs;
+
+size_t spatten_decode_workspace_bytes(int32_t batch, int32_t num_heads, int32_t head_dim);
+int spatten_decode_attn(const SpattenDecodeArgs* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPATTEN_B200_H_ */

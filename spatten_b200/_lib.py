@@ -1,0 +1,77 @@
+"""ctypes binding of the C-ABI library (include/spatten_b200.h).
+
+The product path has no CPU fallback: if `lib/libspatten_b200.so` is missing or a call fails this
+module raises.  Build with `python -c "import __graft_entry__ as g; g.build()"` or
+`make -C spatten_b200/csrc`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libspatten_b200.so")
+
+SPATTEN_OK = 0
+DECODE_PDL = 1
+DECODE_PDL_KV_STABLE = 2
+ERR_NAMES = {-1: "SPATTEN_ERR_INVALID", -2: "SPATTEN_ERR_UNSUPPORTED", -3: "SPATTEN_ERR_CUDA",
+             -4: "SPATTEN_ERR_WORKSPACE"}
+
+
+class SpattenError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+class DecodeArgs(C.Structure):
+    """Mirror of `SpattenDecodeArgs` (include/spatten_b200.h)."""
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("batch", C.c_int32), ("num_heads", C.c_int32), ("num_kv_heads", C.c_int32), ("head_dim", C.c_int32),
+        ("kv_len", C.c_int32), ("rope_len", C.c_int32), ("append", C.c_int32), ("flags", C.c_uint32),
+        ("q", C.c_void_p), ("k_new", C.c_void_p), ("v_new", C.c_void_p),
+        ("k_cache", C.c_void_p), ("v_cache", C.c_void_p),
+        ("cache_stride_b", C.c_int64), ("cache_stride_h", C.c_int64),
+        ("rope", C.c_void_p), ("q_pos", C.c_void_p), ("mask", C.c_void_p), ("head_mask", C.c_void_p),
+        ("out", C.c_void_p), ("logits", C.c_void_p), ("logits_stride", C.c_int64),
+        ("importance", C.c_void_p), ("importance_stride", C.c_int64), ("head_importance", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library once; raise loudly when it is absent (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"spatten_b200: CUDA library not built ({LIB_PATH} missing). Run "
+            "`python -c 'import __graft_entry__ as g; g.build()'` or `make -C spatten_b200/csrc`. "
+            "There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.spatten_abi_version.restype = C.c_int
+    lib.spatten_last_error.restype = C.c_char_p
+    lib.spatten_device_info.argtypes = [C.POINTER(C.c_int)] * 3
+    lib.spatten_decode_workspace_bytes.restype = C.c_size_t
+    lib.spatten_decode_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    lib.spatten_decode_attn.argtypes = [C.POINTER(DecodeArgs), C.c_void_p]
+    _bind_optional(lib)
+    if lib.spatten_abi_version() != 1:
+        raise RuntimeError(f"spatten_b200: ABI version {lib.spatten_abi_version()} != 1")
+    _lib = lib
+    return lib
+
+
+def _bind_optional(lib):
+    pass
+
+
+def check(code: int):
+    if code != SPATTEN_OK:
+        raise SpattenError(code, load().spatten_last_error().decode("utf-8", "replace"))

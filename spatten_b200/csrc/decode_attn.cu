@@ -1,0 +1,675 @@
+// Fused decode attention over the (pruned) KV cache -- spatten_decode_attn().
+//
+// One launch per layer-step does what llama_pos_shift_attention_forward does between the projections
+// for q_len == 1 (reference spatten_llm/pos_shift/modify_llama.py:86-144): RoPE(Q), KV append, RoPE(K at
+// slot index) in registers, Q.K^T/sqrt(D), logit export, mask, fp32 softmax, P.V, and the split-KV merge.
+//
+// Work decomposition (B200: 148 SMs, HBM-bound GEMV-class scan):
+//   * a CTA is 8 independent warps; warp w owns one (batch, head) row and one contiguous token range,
+//     streams that range's K and V rows HBM -> shared memory with 1-D bulk async copies (TMA engine,
+//     cp.async.bulk + mbarrier complete_tx) through a private 6-stage ring, and keeps its own online
+//     softmax state (m, l, acc[D]) in registers.  No CTA-wide barrier in the streaming loop.
+//   * the 8 warps of a CTA work on the SAME token range of 8 different rows, so the RoPE table rows
+//     (shared by all heads) are fetched from L2 once and hit L1 for the other 7 warps.
+//   * the grid is sized to ~one CTA per SM; the host picks the number of token ranges so that
+//     (row groups) x (ranges) fills the SMs evenly.
+//   * each warp writes an (acc, m, l) partial; the last CTA to finish a row group (atomic ticket) merges
+//     the partials, writes fp16 out, and optionally accumulates token / head importance.
+//
+// Tensor cores are deliberately not used here: Llama-2 7B/13B are MHA, so each KV row meets exactly one
+// query row (M = 1); a tcgen05 tile would be >= 63/64 padding and the roofline is HBM bytes, not flops.
+#include <math_constants.h>
+
+#include <algorithm>
+#include <cmath>
+#include <stdio.h>
+
+#include "../../include/spatten_b200.h"
+#include "common.cuh"
+
+namespace spatten {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kPasses = 4;    // a pass = 4 keys x 8 lanes; passes of one tile are independent (ILP)
+constexpr int kTile = 4 * kPasses;  // tokens per pipeline stage (per warp)
+constexpr int kStages = 3;    // ring depth per warp -> 8 warps * 3 * 8 KiB = 192 KiB in flight per SM (D=128)
+constexpr int kMaxPartials = 8192;  // (row, split) partial records the workspace holds
+constexpr int kMaxSplits = 256;     // splits per row the merge handles
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct DecodeParams {
+  const __half* q;
+  const __half* k_new;
+  const __half* v_new;
+  __half* k_cache;
+  __half* v_cache;
+  int64_t stride_b, stride_h;
+  const __half* rope;
+  const int64_t* q_pos;
+  const __half* mask;
+  const uint8_t* head_mask;
+  __half* out;
+  __half* logits;
+  int64_t logits_stride;
+  float* importance;
+  int64_t imp_stride;
+  float* head_importance;
+  float* part;             // [rows][n_splits][D]   un-normalised partial outputs
+  float2* part_ml;         // [rows][n_splits]      (running max, running sum)
+  unsigned int* counters;  // [rows] per-row tickets
+  int H, H_kv, n_rep, kv_len, n_total, append, rope_len;
+  int rows, rpc, spc, n_rg, n_ranges, n_splits, tok_per_split;
+  float sqrt_d, rsqrt_d;
+  int pdl;                 // launched with programmatic stream serialization (SPATTEN_DECODE_PDL)
+  unsigned long long* dbg;  // optional [grid][8 warps][8] globaltimer stamps (tools/microbench.py --timeline)
+};
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define STAMP(k)                                                                                   \
+  do {                                                                                             \
+    if (p.dbg && lane == 0) p.dbg[(static_cast<size_t>(blockIdx.x) * kWarps + warp) * 8 + (k)] = gtime(); \
+  } while (0)
+
+template <int N>
+struct HalfVec {
+  __half2 h[N];
+};
+
+// x / c with the result of an IEEE fp32 division (what torch's fp16 `tensor / sqrt(D)` computes in its fp32
+// opmath, modify_llama.py:111-113) for finite x: one Markstein correction of x * RN(1/c).  Falls back to the
+// uncorrected product when the correction is not finite (x = +-inf).
+__device__ __forceinline__ float div_by_const(float x, float c, float rc) {
+  const float y = x * rc;
+  const float r = fmaf(-y, c, x);
+  const float y2 = fmaf(r, rc, y);
+  return (fabsf(y2) <= 3.4028234e38f) ? y2 : y;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads, 1) decode_attn_kernel(const DecodeParams p) {
+  constexpr int E2 = D / 16;   // halves per lane in each half of the row (8 lanes cover D/2)
+  constexpr int NH2 = E2 / 2;  // half2 per lane per half-row
+  constexpr int VB = E2 * 2;   // bytes per lane per half-row: 16 (D=128) or 8 (D=64)
+  using Vec = typename VecT<VB>::type;
+  using HV = HalfVec<NH2>;
+  constexpr int kRowBytes = D * 2;
+  constexpr int kTileBytes = kTile * kRowBytes;
+  constexpr int kWarpSmem = kStages * 2 * kTileBytes;
+
+  extern __shared__ __align__(128) uint8_t smem[];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 3, c = lane & 7;
+  uint8_t* wsm = smem + warp * kWarpSmem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWarps * kWarpSmem) + warp * kStages;
+
+  // Programmatic dependent launch: let the next kernel in the stream start its own prologue early ...
+  if (p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // ... and, unless the caller vouches that the cached K/V rows and the RoPE table are older than any
+  // kernel still in flight, wait for the previous kernel right here.
+  if (p.pdl != 2) asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  const int rg = blockIdx.x % p.n_rg;
+  const int range = blockIdx.x / p.n_rg;
+  const int row = rg * p.rpc + (warp % p.rpc);
+  const int split = range * p.spc + warp / p.rpc;
+  const bool row_ok = row < p.rows;
+  const int bi = row_ok ? row / p.H : 0;
+  const int h = row_ok ? row % p.H : 0;
+  const int kvh = h / p.n_rep;
+  const bool live = row_ok && (p.head_mask == nullptr || p.head_mask[h] != 0);
+
+  int t0 = split * p.tok_per_split;
+  int t1 = min(t0 + p.tok_per_split, p.n_total);
+  if (!live || t0 >= t1) { t0 = 0; t1 = 0; }
+  const int t1c = min(t1, p.kv_len);                         // cached part of the range
+  const bool owns_new = live && p.append && t1 == p.n_total && t1 > t0;  // slot kv_len is ours
+  const int nt = t1c > t0 ? (t1c - t0 + kTile - 1) / kTile : 0;
+  STAMP(0);
+
+  const __half* Kc = p.k_cache + bi * p.stride_b + kvh * p.stride_h;
+  const __half* Vc = p.v_cache + bi * p.stride_b + kvh * p.stride_h;
+
+  // RoPE rows of one tile: cos | sin for the 4 passes of this lane's key group.  Rows are shared by all
+  // heads, so the other warps of the CTA (same token range) hit L1.
+  auto load_table = [&](int tok0, HV (&cs)[kPasses], HV (&sn)[kPasses]) {
+#pragma unroll
+    for (int ps = 0; ps < kPasses; ++ps) {
+      const int j = min(tok0 + ps * 4 + g, p.rope_len - 1);
+      const __half* r = p.rope + static_cast<int64_t>(j) * D + c * E2;
+      *reinterpret_cast<Vec*>(&cs[ps]) = __ldg(reinterpret_cast<const Vec*>(r));
+      *reinterpret_cast<Vec*>(&sn[ps]) = __ldg(reinterpret_cast<const Vec*>(r + D / 2));
+    }
+  };
+
+  // ---- issue every independent global load first: query, its RoPE row, RoPE rows of tile 0 --------------
+  HV qa, qb, qcs, qsn;
+  auto load_query = [&]() {
+    int64_t pos = p.q_pos ? p.q_pos[bi] : p.kv_len;
+    pos = max(static_cast<int64_t>(0), min(pos, static_cast<int64_t>(p.rope_len - 1)));
+    const __half* qr = p.q + static_cast<int64_t>(row_ok ? row : 0) * D;
+    *reinterpret_cast<Vec*>(&qa) = *reinterpret_cast<const Vec*>(qr + c * E2);
+    *reinterpret_cast<Vec*>(&qb) = *reinterpret_cast<const Vec*>(qr + D / 2 + c * E2);
+    *reinterpret_cast<Vec*>(&qcs) = __ldg(reinterpret_cast<const Vec*>(p.rope + pos * D + c * E2));
+    *reinterpret_cast<Vec*>(&qsn) = __ldg(reinterpret_cast<const Vec*>(p.rope + pos * D + D / 2 + c * E2));
+  };
+  if (p.pdl != 2) load_query();
+  HV cs[kPasses], sn[kPasses];
+  if (nt > 0) load_table(t0, cs, sn);
+
+  // ---- start the K/V stream ---------------------------------------------------------------------------
+  const uint64_t pol = policy_evict_first();
+  auto issue = [&](int i) {
+    const int s = i % kStages;
+    const int tok = t0 + i * kTile;
+    const uint32_t bytes = static_cast<uint32_t>(min(kTile, t1c - tok)) * kRowBytes;
+    mbar_expect_tx(&bars[s], 2 * bytes);
+    bulk_g2s(wsm + s * 2 * kTileBytes, Kc + static_cast<int64_t>(tok) * D, bytes, &bars[s], pol);
+    bulk_g2s(wsm + s * 2 * kTileBytes + kTileBytes, Vc + static_cast<int64_t>(tok) * D, bytes, &bars[s], pol);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+    for (int i = 0; i < min(nt, kStages); ++i) issue(i);
+  }
+  __syncwarp();
+  if (p.pdl == 2) {
+    // K/V prefetch overlapped the previous kernel; everything it may have produced is read after this
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    load_query();
+  }
+
+  // ---- rotate the query at its position id (modify_llama.py:92), fp16 op-for-op, keep as fp32 ---------
+  float ql[E2], qh[E2];
+#pragma unroll
+  for (int i = 0; i < NH2; ++i) {
+    const __half2 rl = __hsub2_rn(__hmul2_rn(qa.h[i], qcs.h[i]), __hmul2_rn(qb.h[i], qsn.h[i]));
+    const __half2 rh = __hadd2_rn(__hmul2_rn(qb.h[i], qcs.h[i]), __hmul2_rn(qa.h[i], qsn.h[i]));
+    const float2 fl = __half22float2(rl), fh = __half22float2(rh);
+    ql[2 * i] = fl.x; ql[2 * i + 1] = fl.y;
+    qh[2 * i] = fh.x; qh[2 * i + 1] = fh.y;
+  }
+  STAMP(1);   // query rotated
+
+  float m = -CUDART_INF_F, l = 0.f;
+  float accl[E2], acch[E2];
+#pragma unroll
+  for (int i = 0; i < E2; ++i) accl[i] = acch[i] = 0.f;
+
+  // this lane's 2*E2 terms of q . rope(k): rotated key rounded to fp16 after every elementwise op (:27),
+  // products summed in fp32 (two chains for ILP); the 8 lanes of the key group are summed by the caller
+  auto rot_dot = [&](const HV& kl, const HV& kh, const HV& c_, const HV& s_) -> float {
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NH2; ++i) {
+      const __half2 rl = __hsub2_rn(__hmul2_rn(kl.h[i], c_.h[i]), __hmul2_rn(kh.h[i], s_.h[i]));
+      const __half2 rh = __hadd2_rn(__hmul2_rn(kh.h[i], c_.h[i]), __hmul2_rn(kl.h[i], s_.h[i]));
+      const float2 fl = __half22float2(rl), fh = __half22float2(rh);
+      d0 = fmaf(ql[2 * i], fl.x, d0);
+      d0 = fmaf(ql[2 * i + 1], fl.y, d0);
+      d1 = fmaf(qh[2 * i], fh.x, d1);
+      d1 = fmaf(qh[2 * i + 1], fh.y, d1);
+    }
+    return d0 + d1;
+  };
+  // fp16 logit exactly as the reference forms it: fp16(matmul) / sqrt(D) -> fp16 (:111-113)
+  auto to_logit = [&](float d) -> __half {
+    return __float2half_rn(div_by_const(__half2float(__float2half_rn(d)), p.sqrt_d, p.rsqrt_d));
+  };
+  auto pv = [&](const HV& vl, const HV& vh, float pr) {
+#pragma unroll
+    for (int i = 0; i < NH2; ++i) {
+      const float2 fl = __half22float2(vl.h[i]), fh = __half22float2(vh.h[i]);
+      accl[2 * i] = fmaf(pr, fl.x, accl[2 * i]);
+      accl[2 * i + 1] = fmaf(pr, fl.y, accl[2 * i + 1]);
+      acch[2 * i] = fmaf(pr, fh.x, acch[2 * i]);
+      acch[2 * i + 1] = fmaf(pr, fh.y, acch[2 * i + 1]);
+    }
+  };
+  __half* lg = p.logits ? p.logits + static_cast<int64_t>(row_ok ? row : 0) * p.logits_stride : nullptr;
+  const __half* mk = p.mask ? p.mask + static_cast<int64_t>(bi) * p.n_total : nullptr;
+
+  // online softmax over kPasses scores per lane (one per key group); m, corr are warp-uniform
+  auto online_update = [&](const float (&sc)[kPasses], float (&pr)[kPasses]) {
+    float mx = sc[0];
+#pragma unroll
+    for (int ps = 1; ps < kPasses; ++ps) mx = fmaxf(mx, sc[ps]);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+    const float m_new = fmaxf(m, mx);
+    if (m_new == -CUDART_INF_F) {             // nothing valid yet
+#pragma unroll
+      for (int ps = 0; ps < kPasses; ++ps) pr[ps] = 0.f;
+      return;
+    }
+    float psum = 0.f;
+#pragma unroll
+    for (int ps = 0; ps < kPasses; ++ps) {
+      pr[ps] = fast_exp2((sc[ps] - m_new) * kLog2e);
+      psum += pr[ps];
+    }
+    if (m_new != m) {                         // warp-uniform: rescale only when the running max moved
+      const float corr = fast_exp2((m - m_new) * kLog2e);
+      l *= corr;
+#pragma unroll
+      for (int i = 0; i < E2; ++i) { accl[i] *= corr; acch[i] *= corr; }
+      m = m_new;
+    }
+    l += psum;
+  };
+
+  // ---- stream the cached tokens --------------------------------------------------------------------
+  for (int i = 0; i < nt; ++i) {
+    const int s = i % kStages;
+    const int tok0 = t0 + i * kTile;
+    const int ntok = min(kTile, t1c - tok0);
+    uint8_t* Ks = wsm + s * 2 * kTileBytes;
+    uint8_t* Vs = Ks + kTileBytes;
+
+    // RoPE rows of the NEXT tile: in flight while this tile is consumed
+    HV csn[kPasses], snn[kPasses];
+    if (i + 1 < nt) load_table(tok0 + kTile, csn, snn);
+
+    if (ntok < kTile) {
+      // zero the rows the partial copy does not write, so masked lanes multiply finite numbers
+      for (int o = ntok * kRowBytes + lane * 16; o < kTileBytes; o += 32 * 16) {
+        *reinterpret_cast<uint4*>(Ks + o) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(Vs + o) = make_uint4(0, 0, 0, 0);
+      }
+      __syncwarp();
+    }
+    mbar_wait(&bars[s], (i / kStages) & 1);
+    if (i == 0) STAMP(2);   // first tile landed
+
+    float d[kPasses];
+#pragma unroll
+    for (int ps = 0; ps < kPasses; ++ps) {
+      const int tl = ps * 4 + g;
+      HV kl, kh;
+      *reinterpret_cast<Vec*>(&kl) = *reinterpret_cast<const Vec*>(Ks + tl * kRowBytes + c * VB);
+      *reinterpret_cast<Vec*>(&kh) = *reinterpret_cast<const Vec*>(Ks + tl * kRowBytes + D + c * VB);
+      d[ps] = rot_dot(kl, kh, cs[ps], sn[ps]);
+    }
+#pragma unroll
+    for (int o = 1; o <= 4; o <<= 1) {
+#pragma unroll
+      for (int ps = 0; ps < kPasses; ++ps) d[ps] += __shfl_xor_sync(0xffffffffu, d[ps], o);
+    }
+    float sc[kPasses], pr[kPasses];
+#pragma unroll
+    for (int ps = 0; ps < kPasses; ++ps) {
+      const int tl = ps * 4 + g;
+      const int j = tok0 + tl;
+      const bool valid = tl < ntok;
+      __half s16 = to_logit(d[ps]);
+      if (valid && c == 0 && lg) lg[j] = s16;
+      if (mk && valid) s16 = __hadd_rn(s16, mk[j]);
+      sc[ps] = valid ? __half2float(s16) : -CUDART_INF_F;
+    }
+    online_update(sc, pr);
+#pragma unroll
+    for (int ps = 0; ps < kPasses; ++ps) {
+      const int tl = ps * 4 + g;
+      HV vl, vh;
+      *reinterpret_cast<Vec*>(&vl) = *reinterpret_cast<const Vec*>(Vs + tl * kRowBytes + c * VB);
+      *reinterpret_cast<Vec*>(&vh) = *reinterpret_cast<const Vec*>(Vs + tl * kRowBytes + D + c * VB);
+      pv(vl, vh, pr[ps]);
+    }
+
+    __syncwarp();                                  // every lane is done reading stage s
+    if (lane == 0 && i + kStages < nt) issue(i + kStages);
+#pragma unroll
+    for (int ps = 0; ps < kPasses; ++ps) { cs[ps] = csn[ps]; sn[ps] = snn[ps]; }
+  }
+  STAMP(3);   // streaming loop done
+
+  // ---- the appended token: read from k_new / v_new, store into slot kv_len (modify_llama.py:95-100) ---
+  if (owns_new) {
+    const int j = p.kv_len;
+    const __half* kn = p.k_new + (static_cast<int64_t>(bi) * p.H_kv + kvh) * D;
+    const __half* vn = p.v_new + (static_cast<int64_t>(bi) * p.H_kv + kvh) * D;
+    HV kl, kh, vl, vh, c1, s1;
+    *reinterpret_cast<Vec*>(&kl) = *reinterpret_cast<const Vec*>(kn + c * E2);
+    *reinterpret_cast<Vec*>(&kh) = *reinterpret_cast<const Vec*>(kn + D / 2 + c * E2);
+    *reinterpret_cast<Vec*>(&vl) = *reinterpret_cast<const Vec*>(vn + c * E2);
+    *reinterpret_cast<Vec*>(&vh) = *reinterpret_cast<const Vec*>(vn + D / 2 + c * E2);
+    const int jr = min(j, p.rope_len - 1);
+    *reinterpret_cast<Vec*>(&c1) = __ldg(reinterpret_cast<const Vec*>(p.rope + static_cast<int64_t>(jr) * D + c * E2));
+    *reinterpret_cast<Vec*>(&s1) =
+        __ldg(reinterpret_cast<const Vec*>(p.rope + static_cast<int64_t>(jr) * D + D / 2 + c * E2));
+    if (g == 0 && (h % p.n_rep) == 0) {            // one writer per kv head
+      __half* kd = p.k_cache + bi * p.stride_b + kvh * p.stride_h + static_cast<int64_t>(j) * D;
+      __half* vd = p.v_cache + bi * p.stride_b + kvh * p.stride_h + static_cast<int64_t>(j) * D;
+      *reinterpret_cast<Vec*>(kd + c * E2) = *reinterpret_cast<Vec*>(&kl);
+      *reinterpret_cast<Vec*>(kd + D / 2 + c * E2) = *reinterpret_cast<Vec*>(&kh);
+      *reinterpret_cast<Vec*>(vd + c * E2) = *reinterpret_cast<Vec*>(&vl);
+      *reinterpret_cast<Vec*>(vd + D / 2 + c * E2) = *reinterpret_cast<Vec*>(&vh);
+    }
+    float d = rot_dot(kl, kh, c1, s1);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 4);
+    __half s16 = to_logit(d);
+    if (lane == 0 && lg) lg[j] = s16;
+    if (mk) s16 = __hadd_rn(s16, mk[j]);
+    float sc[kPasses], pr[kPasses];
+#pragma unroll
+    for (int ps = 0; ps < kPasses; ++ps) sc[ps] = -CUDART_INF_F;
+    if (g == 0) sc[0] = __half2float(s16);          // count it once (key group 0)
+    online_update(sc, pr);
+    pv(vl, vh, pr[0]);
+  }
+
+  // ---- merge the 4 key groups of the warp -------------------------------------------------------------
+  l += __shfl_xor_sync(0xffffffffu, l, 8);
+  l += __shfl_xor_sync(0xffffffffu, l, 16);
+#pragma unroll
+  for (int i = 0; i < E2; ++i) {
+    accl[i] += __shfl_xor_sync(0xffffffffu, accl[i], 8);
+    accl[i] += __shfl_xor_sync(0xffffffffu, accl[i], 16);
+    acch[i] += __shfl_xor_sync(0xffffffffu, acch[i], 8);
+    acch[i] += __shfl_xor_sync(0xffffffffu, acch[i], 16);
+  }
+
+  if (p.n_splits == 1) {
+    // single split: this warp holds the whole row
+    if (row_ok) {
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      float habs = 0.f;
+      if (g == 0) {
+        HV ol, oh;
+#pragma unroll
+        for (int i = 0; i < NH2; ++i) {
+          ol.h[i] = __floats2half2_rn(accl[2 * i] * inv, accl[2 * i + 1] * inv);
+          oh.h[i] = __floats2half2_rn(acch[2 * i] * inv, acch[2 * i + 1] * inv);
+          const float2 a = __half22float2(ol.h[i]), b = __half22float2(oh.h[i]);
+          habs += fabsf(a.x) + fabsf(a.y) + fabsf(b.x) + fabsf(b.y);
+        }
+        __half* o = p.out + static_cast<int64_t>(row) * D;
+        *reinterpret_cast<Vec*>(o + c * E2) = *reinterpret_cast<Vec*>(&ol);
+        *reinterpret_cast<Vec*>(o + D / 2 + c * E2) = *reinterpret_cast<Vec*>(&oh);
+      }
+      if (p.head_importance) {
+        habs = warp_sum(habs);
+        if (lane == 0) atomicAdd(p.head_importance + h, habs);
+      }
+      if (p.importance && lg && live) {
+        __syncwarp();
+        float* imp = p.importance + static_cast<int64_t>(row) * p.imp_stride;
+        for (int j = lane; j < p.n_total; j += 32) {
+          __half s16 = lg[j];
+          if (mk) s16 = __hadd_rn(s16, mk[j]);
+          imp[j] += fast_exp2((__half2float(s16) - m) * kLog2e) * inv;
+        }
+      }
+    }
+    return;
+  }
+
+  if (row_ok && g == 0) {
+    float* rec = p.part + (static_cast<int64_t>(row) * p.n_splits + split) * D;
+#pragma unroll
+    for (int i = 0; i < E2; i += 4) {
+      *reinterpret_cast<float4*>(rec + c * E2 + i) = make_float4(accl[i], accl[i + 1], accl[i + 2], accl[i + 3]);
+      *reinterpret_cast<float4*>(rec + D / 2 + c * E2 + i) = make_float4(acch[i], acch[i + 1], acch[i + 2], acch[i + 3]);
+    }
+    if (c == 0) p.part_ml[static_cast<int64_t>(row) * p.n_splits + split] = make_float2(m, l);
+  }
+
+  // ---- the last warp to finish a row merges that row's partials (per-row ticket) -----------------------
+  STAMP(4);   // partial written
+  __syncwarp();
+  unsigned prev = 0;
+  if (lane == 0 && row_ok) {
+    __threadfence();                                   // release: the warp's partial is visible device-wide
+    prev = atomicAdd(p.counters + row, 1u);
+  }
+  prev = __shfl_sync(0xffffffffu, prev, 0);
+  STAMP(5);   // ticket taken
+  if (!row_ok || prev != static_cast<unsigned>(p.n_splits - 1)) return;
+  __threadfence();                                     // acquire side
+
+  // the K/V ring is dead now: reuse the warp's slice for the split weights
+  float* wts = reinterpret_cast<float*>(wsm);
+  static_assert(kWarpSmem >= kMaxSplits * 4, "ring slice too small for the merge weights");
+  {
+    const float* rec = p.part + static_cast<int64_t>(row) * p.n_splits * D;
+    const float2* ml = p.part_ml + static_cast<int64_t>(row) * p.n_splits;
+    // weights of the splits: all (m, l) loads are independent and issued together
+    constexpr int kPerLane = kMaxSplits / 32;
+    float2 mls[kPerLane];
+#pragma unroll
+    for (int k = 0; k < kPerLane; ++k) {
+      const int sidx = lane + 32 * k;
+      mls[k] = sidx < p.n_splits ? __ldcg(ml + sidx) : make_float2(-CUDART_INF_F, 0.f);
+    }
+    constexpr int PER = D / 32;   // output dims per lane: 4 (D=128) or 2 (D=64)
+    using PV_t = typename VecT<PER * 4>::type;
+    constexpr int kU = 20;        // independent partial loads in flight per lane
+    PV_t v[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u)   // first batch of partials: issued before the weights are known
+      v[u] = __ldcg(reinterpret_cast<const PV_t*>(rec + static_cast<int64_t>(min(u, p.n_splits - 1)) * D + lane * PER));
+    float M = -CUDART_INF_F;
+#pragma unroll
+    for (int k = 0; k < kPerLane; ++k) M = fmaxf(M, mls[k].x);
+    M = warp_max(M);
+    STAMP(7);   // (m, l) of every split arrived
+    float L = 0.f;
+#pragma unroll
+    for (int k = 0; k < kPerLane; ++k) {
+      const int sidx = lane + 32 * k;
+      const float w = (M > -CUDART_INF_F) ? fast_exp2((mls[k].x - M) * kLog2e) : 0.f;
+      if (sidx < p.n_splits) wts[sidx] = w;
+      L = fmaf(mls[k].y, w, L);
+    }
+    L = warp_sum(L);
+    __syncwarp();
+    float o[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) o[i] = 0.f;
+    for (int s0 = 0; s0 < p.n_splits; s0 += kU) {
+      if (s0 > 0) {
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+          v[u] = __ldcg(reinterpret_cast<const PV_t*>(rec + static_cast<int64_t>(min(s0 + u, p.n_splits - 1)) * D + lane * PER));
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const float w = (s0 + u < p.n_splits) ? wts[s0 + u] : 0.f;
+        const float* vf = reinterpret_cast<const float*>(&v[u]);
+#pragma unroll
+        for (int i = 0; i < PER; ++i) o[i] = fmaf(vf[i], w, o[i]);
+      }
+    }
+    const float inv = L > 0.f ? 1.f / L : 0.f;
+    __half oh16[PER];
+    float habs = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      oh16[i] = __float2half_rn(o[i] * inv);
+      habs += fabsf(__half2float(oh16[i]));
+    }
+    __half* od = p.out + static_cast<int64_t>(row) * D + lane * PER;
+    if (PER == 4) *reinterpret_cast<uint2*>(od) = *reinterpret_cast<uint2*>(oh16);
+    else *reinterpret_cast<uint32_t*>(od) = *reinterpret_cast<uint32_t*>(oh16);
+    if (p.head_importance) {
+      habs = warp_sum(habs);
+      if (lane == 0) atomicAdd(p.head_importance + h, habs);
+    }
+    if (p.importance && p.logits && M > -CUDART_INF_F) {
+      float* imp = p.importance + static_cast<int64_t>(row) * p.imp_stride;
+      for (int j = lane; j < p.n_total; j += 32) {
+        __half s16 = __ushort_as_half(__ldcg(reinterpret_cast<const unsigned short*>(lg) + j));
+        if (mk) s16 = __hadd_rn(s16, mk[j]);
+        imp[j] += fast_exp2((__half2float(s16) - M) * kLog2e) * inv;
+      }
+    }
+  }
+  STAMP(6);   // merged
+  if (lane == 0) p.counters[row] = 0;         // self-cleaning ticket for the next launch
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+
+static void choose_split(int rows, int n_total, int sms, int& rpc, int& spc, int& n_rg, int& n_ranges) {
+  rpc = rows >= 8 ? 8 : (rows >= 4 ? 4 : (rows >= 2 ? 2 : 1));
+  spc = kWarps / rpc;
+  n_rg = (rows + rpc - 1) / rpc;
+  const int kMinTok = 16;        // do not cut ranges thinner than this per warp
+  const int kOverheadTok = 24;   // fixed per-CTA cost (prologue, merge) in token-equivalents
+  int max_ranges = (n_total + spc * kMinTok - 1) / (spc * kMinTok);
+  const int rows_pad = n_rg * rpc;
+  max_ranges = std::min(max_ranges, std::max(1, kMaxPartials / (rows_pad * spc)));
+  max_ranges = std::max(1, std::min(max_ranges, kMaxSplits / spc));
+  long best_cost = -1;
+  n_ranges = 1;
+  for (int nr = 1; nr <= max_ranges; ++nr) {
+    const long ctas = static_cast<long>(n_rg) * nr;
+    const long waves = (ctas + sms - 1) / sms;
+    const int tps = (n_total + nr * spc - 1) / (nr * spc);
+    const long cost = waves * (tps + kOverheadTok);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; n_ranges = nr; }
+  }
+}
+
+template <int D>
+static int launch_decode(const DecodeParams& p, cudaStream_t st) {
+  constexpr size_t smem = static_cast<size_t>(kWarps) * kStages * 2 * kTile * D * 2 + kWarps * kStages * 8;
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(decode_attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(decode_attn_kernel)");
+    configured[dev] = true;
+  }
+  cudaError_t e;
+  if (p.pdl) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(p.n_rg * p.n_ranges);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, decode_attn_kernel<D>, p);
+  } else {
+    decode_attn_kernel<D><<<p.n_rg * p.n_ranges, kThreads, smem, st>>>(p);
+    e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "decode_attn_kernel launch");
+  return SPATTEN_OK;
+}
+
+}  // namespace spatten
+
+using namespace spatten;
+
+static unsigned long long* g_dbg = nullptr;
+// Debug hook (not part of the public header): device buffer of [grid][8][8] u64 receiving %globaltimer stamps.
+extern "C" void spatten_debug_set_timeline(unsigned long long* dev_buf) { g_dbg = dev_buf; }
+
+extern "C" size_t spatten_decode_workspace_bytes(int32_t batch, int32_t num_heads, int32_t head_dim) {
+  if (batch <= 0 || num_heads <= 0 || head_dim <= 0) return 0;
+  const size_t counters = (static_cast<size_t>(batch) * num_heads * 4 + 255) / 256 * 256;
+  return counters + static_cast<size_t>(kMaxPartials) * (head_dim + 2) * sizeof(float);  // acc + (m, l)
+}
+
+extern "C" int spatten_decode_attn(const SpattenDecodeArgs* a, void* stream) {
+  SPATTEN_CHECK_ARG(a != nullptr, "spatten_decode_attn: args is NULL");
+  SPATTEN_CHECK_ARG(a->struct_size == sizeof(SpattenDecodeArgs),
+                    "spatten_decode_attn: struct_size %u != %zu (ABI mismatch)", a->struct_size,
+                    sizeof(SpattenDecodeArgs));
+  SPATTEN_CHECK_ARG(a->batch > 0 && a->num_heads > 0 && a->num_kv_heads > 0,
+                    "spatten_decode_attn: batch/num_heads/num_kv_heads must be positive");
+  SPATTEN_CHECK_ARG(a->num_heads % a->num_kv_heads == 0, "spatten_decode_attn: num_heads %d not a multiple of num_kv_heads %d",
+                    a->num_heads, a->num_kv_heads);
+  if (a->head_dim != 64 && a->head_dim != 128) {
+    set_error("spatten_decode_attn: head_dim %d unsupported (64 or 128)", a->head_dim);
+    return SPATTEN_ERR_UNSUPPORTED;
+  }
+  SPATTEN_CHECK_ARG(a->kv_len >= 0 && (a->append == 0 || a->append == 1), "spatten_decode_attn: bad kv_len/append");
+  const int n_total = a->kv_len + a->append;
+  SPATTEN_CHECK_ARG(n_total > 0, "spatten_decode_attn: nothing to attend over (kv_len 0 and append 0)");
+  SPATTEN_CHECK_ARG(a->rope_len >= n_total, "spatten_decode_attn: rope_len %d < kv_len+append %d", a->rope_len, n_total);
+  SPATTEN_CHECK_ARG(a->q && a->k_cache && a->v_cache && a->rope && a->out, "spatten_decode_attn: NULL q/k_cache/v_cache/rope/out");
+  SPATTEN_CHECK_ARG(!a->append || (a->k_new && a->v_new), "spatten_decode_attn: append=1 needs k_new and v_new");
+  SPATTEN_CHECK_ARG(a->cache_stride_h >= static_cast<int64_t>(n_total) * a->head_dim,
+                    "spatten_decode_attn: cache_stride_h %lld too small for %d tokens", (long long)a->cache_stride_h, n_total);
+  SPATTEN_CHECK_ARG(a->cache_stride_b >= a->cache_stride_h * a->num_kv_heads || a->batch == 1,
+                    "spatten_decode_attn: cache_stride_b too small");
+  SPATTEN_CHECK_ARG(a->cache_stride_h % 8 == 0 && a->cache_stride_b % 8 == 0,
+                    "spatten_decode_attn: cache strides must be multiples of 8 elements (16-byte rows)");
+  const uintptr_t al = reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k_cache) |
+                       reinterpret_cast<uintptr_t>(a->v_cache) | reinterpret_cast<uintptr_t>(a->rope) |
+                       reinterpret_cast<uintptr_t>(a->out) | reinterpret_cast<uintptr_t>(a->k_new) |
+                       reinterpret_cast<uintptr_t>(a->v_new);
+  SPATTEN_CHECK_ARG((al & 15) == 0, "spatten_decode_attn: q/k_new/v_new/k_cache/v_cache/rope/out must be 16-byte aligned");
+  SPATTEN_CHECK_ARG(!a->logits || a->logits_stride >= n_total, "spatten_decode_attn: logits_stride < kv_len+append");
+  SPATTEN_CHECK_ARG(!a->importance || (a->logits && a->importance_stride >= n_total),
+                    "spatten_decode_attn: importance needs logits and importance_stride >= kv_len+append");
+
+  DecodeParams p{};
+  p.q = static_cast<const __half*>(a->q);
+  p.k_new = static_cast<const __half*>(a->k_new);
+  p.v_new = static_cast<const __half*>(a->v_new);
+  p.k_cache = static_cast<__half*>(a->k_cache);
+  p.v_cache = static_cast<__half*>(a->v_cache);
+  p.stride_b = a->cache_stride_b;
+  p.stride_h = a->cache_stride_h;
+  p.rope = static_cast<const __half*>(a->rope);
+  p.q_pos = a->q_pos;
+  p.mask = static_cast<const __half*>(a->mask);
+  p.head_mask = a->head_mask;
+  p.out = static_cast<__half*>(a->out);
+  p.logits = static_cast<__half*>(a->logits);
+  p.logits_stride = a->logits_stride;
+  p.importance = a->importance;
+  p.imp_stride = a->importance_stride;
+  p.head_importance = a->head_importance;
+  p.H = a->num_heads;
+  p.H_kv = a->num_kv_heads;
+  p.n_rep = a->num_heads / a->num_kv_heads;
+  p.kv_len = a->kv_len;
+  p.n_total = n_total;
+  p.append = a->append;
+  p.rope_len = a->rope_len;
+  p.rows = a->batch * a->num_heads;
+  p.sqrt_d = static_cast<float>(sqrt(static_cast<double>(a->head_dim)));
+  p.rsqrt_d = 1.0f / p.sqrt_d;
+  p.pdl = 0;
+  if (a->flags & SPATTEN_DECODE_PDL) p.pdl = 1;
+  if ((a->flags & SPATTEN_DECODE_PDL_KV_STABLE) && (a->flags & SPATTEN_DECODE_PDL) && a->head_mask == nullptr) p.pdl = 2;
+  p.dbg = g_dbg;
+
+  const int sms = sm_count();
+  if (sms <= 0) return SPATTEN_ERR_CUDA;
+  choose_split(p.rows, n_total, sms, p.rpc, p.spc, p.n_rg, p.n_ranges);
+  p.n_splits = p.n_ranges * p.spc;
+  p.tok_per_split = (n_total + p.n_splits - 1) / p.n_splits;
+  if (p.n_splits > 1) {
+    const size_t need = spatten_decode_workspace_bytes(a->batch, a->num_heads, a->head_dim);
+    if (a->workspace == nullptr || a->workspace_bytes < need) {
+      set_error("spatten_decode_attn: workspace %zu bytes < required %zu", a->workspace_bytes, need);
+      return SPATTEN_ERR_WORKSPACE;
+    }
+    const size_t counters = (static_cast<size_t>(p.rows) * 4 + 255) / 256 * 256;
+    p.counters = static_cast<unsigned int*>(a->workspace);
+    p.part_ml = reinterpret_cast<float2*>(static_cast<uint8_t*>(a->workspace) + counters);
+    p.part = reinterpret_cast<float*>(static_cast<uint8_t*>(a->workspace) + counters +
+                                      static_cast<size_t>(kMaxPartials) * sizeof(float2));
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return a->head_dim == 128 ? launch_decode<128>(p, st) : launch_decode<64>(p, st);
+}

@@ -8,9 +8,10 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 # north_star: "fp16 attention output within 1e-3 rel".  Measured normwise: max|a-b| / max|b|.
 OUT_REL_TOL = 1e-3
-# exported logits are fp16; one fp16 ulp is 2^-11 = 4.9e-4 relative, so 1e-3 admits a 1-ulp
-# difference from a different fp32 summation order and nothing more.
-LOGIT_REL_TOL = 1e-3
+# exported logits are fp16( fp16(q.k) / sqrt(D) ).  A different fp32 summation order can move the inner
+# fp16 rounding by one ulp (<= 2^-10 relative) and the outer rounding adds half an ulp more, so 2e-3
+# relative is "one ulp of the reference's own intermediate"; tests also require >= 99 % bit-identical.
+LOGIT_REL_TOL = 2e-3
 
 
 def load_golden(kind: str, name: str):
@@ -25,7 +26,7 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
 
 
 def assert_logits_close(mine: torch.Tensor, ref: torch.Tensor, what=""):
-    """Element-wise: |a-b| <= 1e-3*|b| + one fp16 subnormal-ish floor (values near 0)."""
+    """Element-wise: |a-b| <= LOGIT_REL_TOL*|b| + 1e-4 (floor for values near 0)."""
     a, b = mine.double().cpu(), ref.double().cpu()
     finite = torch.isfinite(b)
     bad = ((a - b).abs() > LOGIT_REL_TOL * b.abs() + 1e-4) & finite

@@ -1,0 +1,116 @@
+"""Kernel-level timing of spatten_decode_attn on synthetic Llama-shaped caches (CUDA graph + events)."""
+import argparse
+import json
+import sys
+import os
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from spatten_b200 import ops  # noqa: E402
+
+
+def bench_shape(b, H, D, n, L, iters, logits_on=True, graph=True, flags=0):
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(1)
+    kc = [torch.randn((b, H, n + 8, D), generator=g, device=dev, dtype=torch.float16) for _ in range(L)]
+    vc = [torch.randn((b, H, n + 8, D), generator=g, device=dev, dtype=torch.float16) for _ in range(L)]
+    q = torch.randn((L, b, H, D), generator=g, device=dev, dtype=torch.float16)
+    kn = torch.randn((L, b, H, D), generator=g, device=dev, dtype=torch.float16)
+    vn = torch.randn((L, b, H, D), generator=g, device=dev, dtype=torch.float16)
+    rope = ops.rope_table(D, n + 8, dev)
+    out = torch.empty((L, b, H, D), device=dev, dtype=torch.float16)
+    logits = torch.empty((L, b, H, n + 8), device=dev, dtype=torch.float16) if logits_on else None
+
+    def step():
+        for l in range(L):
+            ops.decode_attn(q[l], kc[l], vc[l], n - 1, rope, k_new=kn[l], v_new=vn[l],
+                            logits=None if logits is None else logits[l], out=out[l], flags=flags)
+
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            step()
+        s.synchronize()
+        if graph:
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=s):
+                step()
+            run = gr.replay
+        else:
+            run = step
+        for _ in range(3):
+            run()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.synchronize()
+        e0.record(s)
+        for _ in range(iters):
+            run()
+        e1.record(s)
+        s.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    bytes_layer = 2 * b * H * n * D * 2
+    us_layer = ms * 1e3 / L
+    return {"b": b, "H": H, "D": D, "n": n, "L": L, "logits": logits_on, "graph": graph, "flags": flags,
+            "us_per_layer": round(us_layer, 3), "GBps": round(bytes_layer / us_layer / 1e3, 1),
+            "frac_6445": round(bytes_layer / us_layer / 1e3 / 6445, 4)}
+
+
+def timeline(b, H, D, n, L):
+    """Phase timeline of the LAST of L back-to-back launches (warm caches), from %globaltimer stamps."""
+    import ctypes as C
+    import numpy as np
+    from spatten_b200 import _lib
+    lib = _lib.load()
+    dev = "cuda"
+    buf = torch.zeros(4096 * 8 * 8, dtype=torch.int64, device=dev)
+    g = torch.Generator(device=dev).manual_seed(1)
+    kc = [torch.randn((b, H, n + 8, D), generator=g, device=dev, dtype=torch.float16) for _ in range(L)]
+    vc = [torch.randn((b, H, n + 8, D), generator=g, device=dev, dtype=torch.float16) for _ in range(L)]
+    q = torch.randn((L, b, H, D), generator=g, device=dev, dtype=torch.float16)
+    rope = ops.rope_table(D, n + 8, dev)
+    logits = torch.empty((L, b, H, n + 8), device=dev, dtype=torch.float16)
+    for rep in range(3):
+        for l in range(L):
+            if rep == 2 and l == L - 1:
+                lib.spatten_debug_set_timeline(C.c_void_p(buf.data_ptr()))
+            ops.decode_attn(q[l], kc[l], vc[l], n - 1, rope, k_new=q[l], v_new=q[l], logits=logits[l])
+    torch.cuda.synchronize()
+    lib.spatten_debug_set_timeline(None)
+    t = buf.cpu().numpy().reshape(-1, 8, 8).astype(np.float64)
+    used = t[:, :, 0].max(axis=1) > 0
+    t = t[used]
+    t0 = t[:, :, 0][t[:, :, 0] > 0].min()
+    names = ["start", "q_rotated", "tile0_landed", "loop_done", "partial_written", "ticket", "merged", "ml_arrived"]
+    print(f"timeline b={b} H={H} D={D} n={n}: {t.shape[0]} CTAs; ns relative to first warp start")
+    for k, nm in enumerate(names):
+        v = t[:, :, k]
+        v = v[v > 0] - t0
+        if k >= 6:   # merge-only stamps: report relative to the same warp's ticket stamp
+            sel = t[:, :, k] > 0
+            dv = (t[:, :, k] - t[:, :, 5])[sel]
+            print(f"  {nm:16s} after own ticket: min {dv.min():6.0f} median {np.median(dv):6.0f} max {dv.max():6.0f}")
+        if v.size:
+            print(f"  {nm:16s} min {v.min():8.0f}  median {np.median(v):8.0f}  max {v.max():8.0f}  (n={v.size})")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=50)
+    ap.add_argument("--shape", type=str, default=None, help="b,H,D,n,L: run only this shape (for ncu)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--timeline", action="store_true", help="dump per-phase globaltimer stamps for one launch")
+    a = ap.parse_args()
+    if a.timeline:
+        timeline(*map(int, (a.shape or "1,32,128,2048,32").split(",")))
+        sys.exit(0)
+    if a.shape:
+        b, H, D, n, L = map(int, a.shape.split(","))
+        print(json.dumps(bench_shape(b, H, D, n, L, a.iters, True, graph=not a.no_graph)), flush=True)
+        sys.exit(0)
+    shapes = [(1, 32, 128, 2048, 32), (1, 32, 128, 4096, 32), (1, 32, 128, 8192, 16), (8, 5, 128, 16384, 8),
+              (1, 4, 128, 2048, 32), (1, 32, 128, 512, 32)]
+    for (b, H, D, n, L) in shapes:
+        for fl in (0, 1, 3):
+            print(json.dumps(bench_shape(b, H, D, n, L, a.iters, True, flags=fl)), flush=True)
+    print(json.dumps(bench_shape(1, 32, 128, 2048, 32, a.iters, True, graph=False)), flush=True)
