@@ -72,9 +72,13 @@ typedef struct SpattenDecodeArgs {
   int32_t rope_len;       /* rows in `rope`; must be >= kv_len + 1 and > every q_pos */
   int32_t append;         /* 1: write k_new/v_new into slot kv_len and attend over kv_len+1 tokens
                              (reference behaviour); 0: attend over the kv_len cached tokens only */
-  uint32_t flags;         /* SPATTEN_DECODE_* bits below */
+  uint32_t flags;         /* SPATTEN_DECODE_* bits above */
+  int32_t q_len;          /* query rows per sequence.  1 (or 0) = decode.  > 1 = a prefill / chunk: every query
+                             row is scored against ALL kv_len cached tokens (the reference exports the full
+                             pre-mask [q, kv] logit matrix, :111-119, and masks additively, :127-132); requires
+                             append == 0, i.e. the caller has already stored the new K/V rows in the cache */
 
-  const void* q;          /* fp16 [b, H, D]      un-rotated query of the new token (after q_proj) */
+  const void* q;          /* fp16 [b, q_len, H, D]  un-rotated queries (q_proj output viewed, NOT transposed) */
   const void* k_new;      /* fp16 [b, H_kv, D]   un-rotated key   (append == 1) */
   const void* v_new;      /* fp16 [b, H_kv, D]   value            (append == 1) */
   void* k_cache;          /* fp16 [b, H_kv, >=kv_len+append, D] un-rotated keys, strides below */
@@ -83,13 +87,15 @@ typedef struct SpattenDecodeArgs {
   int64_t cache_stride_h; /* elements between kv heads (= capacity * D for a preallocated cache) */
   const void* rope;       /* fp16 [rope_len, D]: row p = cos(p*theta_i) i<D/2 | sin(p*theta_i) i<D/2,
                              i.e. the first halves of HF-4.33 LlamaRotaryEmbedding's cos/sin rows (:89) */
-  const int64_t* q_pos;   /* [b] position_ids of the query (:92); NULL = kv_len */
-  const void* mask;       /* optional fp16 additive mask [b, kv_len+append] (:127-132); NULL = none */
+  const int64_t* q_pos;   /* [b, q_len] position_ids of the queries (:92); NULL = kv_len (decode only) */
+  const void* mask;       /* optional fp16 additive mask [b, q_len, kv_len+append] (:127-132); NULL = none */
   const uint8_t* head_mask; /* optional [H]; 0 = pruned head: no KV read, output row zeroed */
 
-  void* out;              /* fp16 [b, H, D] == attn_output[b, 1, H*D] before o_proj (:146-147) */
-  void* logits;           /* optional fp16 [b, H, logits_stride]: attn_scores[b,h,0,:] (:116-119) */
-  int64_t logits_stride;  /* elements between (b,h) rows of `logits` (>= kv_len+append) */
+  void* out;              /* fp16 [b, q_len, H, D] == attn_output[b, q_len, H*D] before o_proj (:146-147) */
+  void* logits;           /* optional fp16 attn_scores[b, h, q, :] (:116-119), strides below */
+  int64_t logits_stride;  /* elements between heads   (>= kv_len+append) */
+  int64_t logits_stride_b;/* elements between sequences; 0 = num_heads * logits_stride (decode layout) */
+  int64_t logits_stride_q;/* elements between query rows; ignored when q_len <= 1 */
   float* importance;      /* optional fp32 [b, H, importance_stride]: += softmax probability
                              (cumulative token importance, README.md:21) */
   int64_t importance_stride;
@@ -102,6 +108,67 @@ typedef struct SpattenDecodeArgs {
 
 size_t spatten_decode_workspace_bytes(int32_t batch, int32_t num_heads, int32_t head_dim);
 int spatten_decode_attn(const SpattenDecodeArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * KV-cache token pruning.  Replaces SpAttenKVCache.apply_token_pruning
+ * (spatten_llm/kv_cache_token_pruning.py:42-96) with three device-side steps and no host sync
+ * (the reference synchronises once per layer through `.cpu()`, :66).
+ * ---------------------------------------------------------------------------------------------- */
+#define SPATTEN_DTYPE_F16 0
+#define SPATTEN_DTYPE_F32 1
+
+/* Host-only arithmetic of :45-47, :59, :78-80.  Returns 1 when seq_len + num_coming already fits in
+ * start+important+recent (the reference returns past_key_values unchanged, :46-47), SPATTEN_OK (0) when
+ * pruning applies -- then *keep_total = start + important + max(0, seq_len - win_end) and the candidate
+ * window is [win_begin, win_end) = [start, min(seq_len, seq_len - recent + num_coming)) -- or
+ * SPATTEN_ERR_INVALID for important <= 0 (reference: TypeError at :63) and for a window shorter than
+ * `important` (reference: RuntimeError "selected index k out of range" from torch.topk, :60). */
+int spatten_prune_plan(int32_t seq_len, int32_t num_coming, int32_t start, int32_t important, int32_t recent,
+                       int32_t* keep_total, int32_t* win_begin, int32_t* win_end);
+
+/* importance_score = attn_scores.sum(0).sum(1) (:51): [b, H, q, S] -> [H, S], summed over batch then
+ * over query in fp32 and rounded to the score dtype after each of the two sums, as torch does.
+ * Strides in elements; the innermost (S) dimension is contiguous. */
+int spatten_score_reduce(const void* scores, int32_t dtype, int32_t b, int32_t H, int32_t q, int32_t S,
+                         int64_t stride_b, int64_t stride_h, int64_t stride_q, void* out, int64_t out_stride,
+                         void* stream);
+
+/* Per score row: the kept token list  [0,start) U top-`important` of score[win_begin:win_end) U
+ * [win_end, seq_len)  in ascending order (:59-63 topk + sort, :74-93 the three cat pieces).
+ * Ties at the k-th value are broken lowest-index-first (the RTL engine's rule, TopK.scala:159-160,
+ * 209-211); torch.topk leaves the choice unspecified.  One CTA per row: 8-bit radix select on
+ * order-preserving keys with warp-aggregated histograms, then a ballot/prefix-sum compaction. */
+typedef struct SpattenSelectArgs {
+  uint32_t struct_size;
+  int32_t num_rows;       /* independent rows (heads of one layer, or layers*heads) */
+  int32_t seq_len;        /* S */
+  int32_t num_coming, start, important, recent;
+  int32_t score_dtype;    /* SPATTEN_DTYPE_F16 / _F32 */
+  const void* score;      /* [num_rows, score_stride] */
+  int64_t score_stride;   /* elements, >= seq_len */
+  int32_t* keep_idx;      /* out [num_rows, keep_stride], first keep_total entries written */
+  int64_t keep_stride;    /* elements, >= keep_total */
+} SpattenSelectArgs;
+int spatten_topk_select(const SpattenSelectArgs* args, void* stream);
+
+/* dst[b, h, p, :] = src[b, h, keep_idx[h, p], :] for K and V (:65-93; the bool-mask gather plus the two
+ * cat()s).  The same per-head index list is applied to every sequence of the batch (the reference sums the
+ * score over the batch, :51, and itself only runs for batch 1, :68).  Byte strides, rows of `row_bytes`
+ * contiguous bytes (multiple of 16, <= 512) -- dtype-agnostic, so fp16, fp32 and packed int4/int8 planes
+ * all go through it.  src == dst (same strides) compacts IN PLACE. */
+typedef struct SpattenGatherArgs {
+  uint32_t struct_size;
+  int32_t batch, num_heads, keep_total, row_bytes;
+  const void* src_k;
+  const void* src_v;
+  int64_t src_stride_b, src_stride_h;   /* bytes */
+  void* dst_k;
+  void* dst_v;
+  int64_t dst_stride_b, dst_stride_h;   /* bytes */
+  const int32_t* keep_idx;              /* [num_heads, keep_stride] ascending */
+  int64_t keep_stride;
+} SpattenGatherArgs;
+int spatten_kv_gather(const SpattenGatherArgs* args, void* stream);
 
 #ifdef __cplusplus
 }

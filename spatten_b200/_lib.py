@@ -30,16 +30,41 @@ class DecodeArgs(C.Structure):
     _fields_ = [
         ("struct_size", C.c_uint32),
         ("batch", C.c_int32), ("num_heads", C.c_int32), ("num_kv_heads", C.c_int32), ("head_dim", C.c_int32),
-        ("kv_len", C.c_int32), ("rope_len", C.c_int32), ("append", C.c_int32), ("flags", C.c_uint32),
+        ("kv_len", C.c_int32), ("rope_len", C.c_int32), ("append", C.c_int32), ("flags", C.c_uint32), ("q_len", C.c_int32),
         ("q", C.c_void_p), ("k_new", C.c_void_p), ("v_new", C.c_void_p),
         ("k_cache", C.c_void_p), ("v_cache", C.c_void_p),
         ("cache_stride_b", C.c_int64), ("cache_stride_h", C.c_int64),
         ("rope", C.c_void_p), ("q_pos", C.c_void_p), ("mask", C.c_void_p), ("head_mask", C.c_void_p),
         ("out", C.c_void_p), ("logits", C.c_void_p), ("logits_stride", C.c_int64),
+        ("logits_stride_b", C.c_int64), ("logits_stride_q", C.c_int64),
         ("importance", C.c_void_p), ("importance_stride", C.c_int64), ("head_importance", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
+
+class SelectArgs(C.Structure):
+    """Mirror of `SpattenSelectArgs`."""
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("num_rows", C.c_int32), ("seq_len", C.c_int32),
+        ("num_coming", C.c_int32), ("start", C.c_int32), ("important", C.c_int32), ("recent", C.c_int32),
+        ("score_dtype", C.c_int32),
+        ("score", C.c_void_p), ("score_stride", C.c_int64),
+        ("keep_idx", C.c_void_p), ("keep_stride", C.c_int64),
+    ]
+
+
+class GatherArgs(C.Structure):
+    """Mirror of `SpattenGatherArgs`."""
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("batch", C.c_int32), ("num_heads", C.c_int32), ("keep_total", C.c_int32),
+        ("row_bytes", C.c_int32),
+        ("src_k", C.c_void_p), ("src_v", C.c_void_p), ("src_stride_b", C.c_int64), ("src_stride_h", C.c_int64),
+        ("dst_k", C.c_void_p), ("dst_v", C.c_void_p), ("dst_stride_b", C.c_int64), ("dst_stride_h", C.c_int64),
+        ("keep_idx", C.c_void_p), ("keep_stride", C.c_int64),
+    ]
+
+
+DTYPE_F16, DTYPE_F32 = 0, 1
 
 _lib = None
 
@@ -69,7 +94,11 @@ def load() -> C.CDLL:
 
 
 def _bind_optional(lib):
-    pass
+    lib.spatten_prune_plan.argtypes = [C.c_int32] * 5 + [C.POINTER(C.c_int32)] * 3
+    lib.spatten_score_reduce.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.spatten_topk_select.argtypes = [C.POINTER(SelectArgs), C.c_void_p]
+    lib.spatten_kv_gather.argtypes = [C.POINTER(GatherArgs), C.c_void_p]
 
 
 def check(code: int):

@@ -36,6 +36,7 @@ constexpr int kTile = 4 * kPasses;  // tokens per pipeline stage (per warp)
 constexpr int kStages = 3;    // ring depth per warp -> 8 warps * 3 * 8 KiB = 192 KiB in flight per SM (D=128)
 constexpr int kMaxPartials = 8192;  // (row, split) partial records the workspace holds
 constexpr int kMaxSplits = 256;     // splits per row the merge handles
+constexpr size_t kTicketBytes = static_cast<size_t>(kMaxPartials) * sizeof(unsigned int);  // per-row tickets
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct DecodeParams {
@@ -59,6 +60,8 @@ struct DecodeParams {
   float2* part_ml;         // [rows][n_splits]      (running max, running sum)
   unsigned int* counters;  // [rows] per-row tickets
   int H, H_kv, n_rep, kv_len, n_total, append, rope_len;
+  int q_len;                        // query rows per sequence (1 = decode; > 1 = prefill rows, append == 0)
+  int64_t logits_stride_b, logits_stride_q;
   int rows, rpc, spc, n_rg, n_ranges, n_splits, tok_per_split;
   float sqrt_d, rsqrt_d;
   int pdl;                 // launched with programmatic stream serialization (SPATTEN_DECODE_PDL)
@@ -119,8 +122,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_attn_kernel(const DecodePa
   const int row = rg * p.rpc + (warp % p.rpc);
   const int split = range * p.spc + warp / p.rpc;
   const bool row_ok = row < p.rows;
-  const int bi = row_ok ? row / p.H : 0;
+  const int bq = row_ok ? row / p.H : 0;      // (sequence, query) pair: indexes q, q_pos, mask, out
   const int h = row_ok ? row % p.H : 0;
+  const int bi = bq / p.q_len;                 // sequence: indexes the KV cache
   const int kvh = h / p.n_rep;
   const bool live = row_ok && (p.head_mask == nullptr || p.head_mask[h] != 0);
 
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_attn_kernel(const DecodePa
   // ---- issue every independent global load first: query, its RoPE row, RoPE rows of tile 0 --------------
   HV qa, qb, qcs, qsn;
   auto load_query = [&]() {
-    int64_t pos = p.q_pos ? p.q_pos[bi] : p.kv_len;
+    int64_t pos = p.q_pos ? p.q_pos[bq] : p.kv_len;
     pos = max(static_cast<int64_t>(0), min(pos, static_cast<int64_t>(p.rope_len - 1)));
     const __half* qr = p.q + static_cast<int64_t>(row_ok ? row : 0) * D;
     *reinterpret_cast<Vec*>(&qa) = *reinterpret_cast<const Vec*>(qr + c * E2);
@@ -232,8 +236,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_attn_kernel(const DecodePa
       acch[2 * i + 1] = fmaf(pr, fh.y, acch[2 * i + 1]);
     }
   };
-  __half* lg = p.logits ? p.logits + static_cast<int64_t>(row_ok ? row : 0) * p.logits_stride : nullptr;
-  const __half* mk = p.mask ? p.mask + static_cast<int64_t>(bi) * p.n_total : nullptr;
+  __half* lg = p.logits ? p.logits + bi * p.logits_stride_b + h * p.logits_stride + (bq % p.q_len) * p.logits_stride_q
+                        : nullptr;
+  const __half* mk = p.mask ? p.mask + static_cast<int64_t>(bq) * p.n_total : nullptr;
 
   // online softmax over kPasses scores per lane (one per key group); m, corr are warp-uniform
   auto online_update = [&](const float (&sc)[kPasses], float (&pr)[kPasses]) {
@@ -582,8 +587,9 @@ extern "C" void spatten_debug_set_timeline(unsigned long long* dev_buf) { g_dbg 
 
 extern "C" size_t spatten_decode_workspace_bytes(int32_t batch, int32_t num_heads, int32_t head_dim) {
   if (batch <= 0 || num_heads <= 0 || head_dim <= 0) return 0;
-  const size_t counters = (static_cast<size_t>(batch) * num_heads * 4 + 255) / 256 * 256;
-  return counters + static_cast<size_t>(kMaxPartials) * (head_dim + 2) * sizeof(float);  // acc + (m, l)
+  // fixed layout, independent of batch/heads, so one zero-initialised workspace serves every shape:
+  // [tickets: kTicketBytes][(m, l): kMaxPartials float2][acc: kMaxPartials * head_dim floats]
+  return kTicketBytes + static_cast<size_t>(kMaxPartials) * (head_dim + 2) * sizeof(float);
 }
 
 extern "C" int spatten_decode_attn(const SpattenDecodeArgs* a, void* stream) {
@@ -601,6 +607,12 @@ extern "C" int spatten_decode_attn(const SpattenDecodeArgs* a, void* stream) {
   }
   SPATTEN_CHECK_ARG(a->kv_len >= 0 && (a->append == 0 || a->append == 1), "spatten_decode_attn: bad kv_len/append");
   const int n_total = a->kv_len + a->append;
+  const int q_len = a->q_len > 1 ? a->q_len : 1;
+  SPATTEN_CHECK_ARG(q_len == 1 || (a->append == 0 && a->q_pos != nullptr && a->importance == nullptr),
+                    "spatten_decode_attn: q_len > 1 needs append == 0, q_pos, and no importance accumulation");
+  SPATTEN_CHECK_ARG(q_len == 1 || !a->logits || a->logits_stride_q >= n_total,
+                    "spatten_decode_attn: logits_stride_q < kv_len");
+  SPATTEN_CHECK_ARG(static_cast<int64_t>(a->batch) * q_len * a->num_heads < (1ll << 31), "spatten_decode_attn: too many rows");
   SPATTEN_CHECK_ARG(n_total > 0, "spatten_decode_attn: nothing to attend over (kv_len 0 and append 0)");
   SPATTEN_CHECK_ARG(a->rope_len >= n_total, "spatten_decode_attn: rope_len %d < kv_len+append %d", a->rope_len, n_total);
   SPATTEN_CHECK_ARG(a->q && a->k_cache && a->v_cache && a->rope && a->out, "spatten_decode_attn: NULL q/k_cache/v_cache/rope/out");
@@ -635,6 +647,9 @@ extern "C" int spatten_decode_attn(const SpattenDecodeArgs* a, void* stream) {
   p.out = static_cast<__half*>(a->out);
   p.logits = static_cast<__half*>(a->logits);
   p.logits_stride = a->logits_stride;
+  p.q_len = q_len;
+  p.logits_stride_b = a->logits_stride_b ? a->logits_stride_b : a->logits_stride * a->num_heads;
+  p.logits_stride_q = q_len > 1 ? a->logits_stride_q : 0;
   p.importance = a->importance;
   p.imp_stride = a->importance_stride;
   p.head_importance = a->head_importance;
@@ -645,7 +660,7 @@ extern "C" int spatten_decode_attn(const SpattenDecodeArgs* a, void* stream) {
   p.n_total = n_total;
   p.append = a->append;
   p.rope_len = a->rope_len;
-  p.rows = a->batch * a->num_heads;
+  p.rows = a->batch * q_len * a->num_heads;
   p.sqrt_d = static_cast<float>(sqrt(static_cast<double>(a->head_dim)));
   p.rsqrt_d = 1.0f / p.sqrt_d;
   p.pdl = 0;
@@ -664,7 +679,8 @@ extern "C" int spatten_decode_attn(const SpattenDecodeArgs* a, void* stream) {
       set_error("spatten_decode_attn: workspace %zu bytes < required %zu", a->workspace_bytes, need);
       return SPATTEN_ERR_WORKSPACE;
     }
-    const size_t counters = (static_cast<size_t>(p.rows) * 4 + 255) / 256 * 256;
+    // split rows are bounded by the partial budget (rows * n_splits <= kMaxPartials, n_splits >= 2)
+    const size_t counters = kTicketBytes;
     p.counters = static_cast<unsigned int*>(a->workspace);
     p.part_ml = reinterpret_cast<float2*>(static_cast<uint8_t*>(a->workspace) + counters);
     p.part = reinterpret_cast<float*>(static_cast<uint8_t*>(a->workspace) + counters +

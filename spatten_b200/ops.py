@@ -52,17 +52,23 @@ def decode_attn(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, k
                 head_mask: Optional[torch.Tensor] = None, logits: Optional[torch.Tensor] = None,
                 importance: Optional[torch.Tensor] = None, head_importance: Optional[torch.Tensor] = None,
                 out: Optional[torch.Tensor] = None, flags: int = 0) -> torch.Tensor:
-    """One decode step of attention for every (batch, head) row -- `spatten_decode_attn`.
+    """Attention of new-token queries against the KV cache -- `spatten_decode_attn`.
 
-    q [b,H,D] fp16 un-rotated; k_cache/v_cache [b,H_kv,cap,D] fp16 (any batch/head strides, rows
+    q: fp16 [b,H,D] (decode) or [b,q_len,H,D] (prefill rows; the new K/V must already be in the cache
+    and k_new must be None); k_cache/v_cache [b,H_kv,cap,D] fp16 (any batch/head strides, rows
     contiguous); kv_len tokens valid; k_new/v_new [b,H_kv,D] appended at slot kv_len when given.
-    Returns out [b,H,D] fp16.  `logits` [b,H,>=n] receives attn_scores; `importance` fp32 [b,H,>=n]
-    and `head_importance` fp32 [H] are accumulated in place.
+    q_pos int64 [b] / [b,q_len]; mask fp16 [b,n] / [b,q_len,n] additive.
+    Returns out fp16 with q's shape.  `logits` receives attn_scores: [b,H,>=n] (decode) or
+    [b,H,q_len,>=n]; `importance` fp32 [b,H,>=n] and `head_importance` fp32 [H] accumulate in place.
     """
     lib = _lib.load()
     _require_cuda(q, k_cache, v_cache, rope, k_new, v_new, q_pos, mask, head_mask, logits, importance,
                   head_importance, out)
-    b, H, D = q.shape
+    if q.dim() == 3:
+        b, H, D = q.shape
+        q_len = 1
+    else:
+        b, q_len, H, D = q.shape
     H_kv = k_cache.shape[1]
     if q.dtype != torch.float16 or k_cache.dtype != torch.float16 or v_cache.dtype != torch.float16:
         raise TypeError("spatten_b200.decode_attn: fp16 tensors required")
@@ -71,38 +77,157 @@ def decode_attn(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, k
     if not q.is_contiguous():
         q = q.contiguous()
     append = k_new is not None
+    n_total = int(kv_len) + int(append)
     if append:
         k_new, v_new = k_new.contiguous(), v_new.contiguous()
     if out is None:
-        out = torch.empty((b, H, D), dtype=torch.float16, device=q.device)
+        out = torch.empty(q.shape, dtype=torch.float16, device=q.device)
+    elif not out.is_contiguous() or out.numel() != q.numel():
+        raise ValueError("out must be contiguous with q's shape")
     a = _lib.DecodeArgs()
     a.struct_size = C.sizeof(_lib.DecodeArgs)
     a.batch, a.num_heads, a.num_kv_heads, a.head_dim = b, H, H_kv, D
-    a.kv_len, a.rope_len, a.append, a.flags = int(kv_len), rope.shape[0], int(append), int(flags)
+    a.kv_len, a.rope_len, a.append, a.flags, a.q_len = int(kv_len), rope.shape[0], int(append), int(flags), q_len
     a.q, a.k_cache, a.v_cache = q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr()
     a.k_new = k_new.data_ptr() if append else None
     a.v_new = v_new.data_ptr() if append else None
     a.cache_stride_b, a.cache_stride_h = k_cache.stride(0), k_cache.stride(1)
     a.rope = rope.data_ptr()
     if q_pos is not None:
-        if q_pos.dtype != torch.int64:
-            raise TypeError("q_pos must be int64 (HF position_ids)")
-        a.q_pos = q_pos.contiguous().data_ptr()
+        if q_pos.dtype != torch.int64 or q_pos.numel() != b * q_len:
+            raise TypeError("q_pos must be int64 with b*q_len entries (HF position_ids)")
+        q_pos = q_pos.contiguous()
+        a.q_pos = q_pos.data_ptr()
     if mask is not None:
-        if mask.dtype != torch.float16 or mask.shape != (b, kv_len + int(append)) or not mask.is_contiguous():
-            raise ValueError("mask must be contiguous fp16 [b, kv_len+append]")
+        if mask.dtype != torch.float16 or mask.numel() != b * q_len * n_total or not mask.is_contiguous():
+            raise ValueError("mask must be contiguous fp16 [b, q_len, kv_len+append]")
         a.mask = mask.data_ptr()
     if head_mask is not None:
         a.head_mask = head_mask.data_ptr()
     a.out = out.data_ptr()
     if logits is not None:
-        a.logits, a.logits_stride = logits.data_ptr(), logits.stride(1)
+        if logits.dtype != torch.float16 or logits.stride(-1) != 1:
+            raise ValueError("logits must be fp16 with a contiguous last dimension")
+        a.logits, a.logits_stride_b, a.logits_stride = logits.data_ptr(), logits.stride(0), logits.stride(1)
+        if q_len > 1:
+            a.logits_stride_q = logits.stride(2)
     if importance is not None:
         a.importance, a.importance_stride = importance.data_ptr(), importance.stride(1)
     if head_importance is not None:
         a.head_importance = head_importance.data_ptr()
-    ws = decode_workspace(q.device, b, H, D)
+    ws = decode_workspace(q.device, b * q_len, H, D)
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     with torch.cuda.device(q.device):
         _lib.check(lib.spatten_decode_attn(C.byref(a), C.c_void_p(_stream_ptr(q.device))))
     return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# token pruning
+# ------------------------------------------------------------------------------------------------------
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float16:
+        return _lib.DTYPE_F16
+    if t.dtype == torch.float32:
+        return _lib.DTYPE_F32
+    raise TypeError(f"spatten_b200: scores must be fp16 or fp32, got {t.dtype}")
+
+
+def prune_plan(seq_len: int, num_coming: int, start: int, important: int, recent: int):
+    """Host arithmetic of the reference's prune (kv_cache_token_pruning.py:45-47,59,78-80).
+
+    Returns None when the cache already fits, else (keep_total, win_begin, win_end).  Raises what the
+    reference raises: TypeError for important_size == 0 (:63), RuntimeError when the candidate window
+    is shorter than `important` (torch.topk, :60).
+    """
+    lib = _lib.load()
+    kt, wb, we = C.c_int32(), C.c_int32(), C.c_int32()
+    rc = lib.spatten_prune_plan(seq_len, num_coming, start, important, recent, C.byref(kt), C.byref(wb), C.byref(we))
+    if rc == 1:
+        return None
+    if rc != 0:
+        msg = lib.spatten_last_error().decode()
+        if "important_size" in msg:
+            raise TypeError(msg)
+        raise RuntimeError(msg)
+    return kt.value, wb.value, we.value
+
+
+def score_reduce(attn_scores: torch.Tensor) -> torch.Tensor:
+    """[b,H,q,S] -> [H,S] == attn_scores.sum(0).sum(1) (kv_cache_token_pruning.py:51)."""
+    lib = _lib.load()
+    _require_cuda(attn_scores)
+    b, H, q, S = attn_scores.shape
+    if attn_scores.stride(3) != 1:
+        attn_scores = attn_scores.contiguous()
+    if b == 1 and q == 1:
+        return attn_scores[0, :, 0, :]          # both sums are over singleton dims: exact identity
+    out = torch.empty((H, S), dtype=attn_scores.dtype, device=attn_scores.device)
+    with torch.cuda.device(attn_scores.device):
+        _lib.check(lib.spatten_score_reduce(attn_scores.data_ptr(), _dtype_code(attn_scores), b, H, q, S,
+                                            attn_scores.stride(0), attn_scores.stride(1), attn_scores.stride(2),
+                                            out.data_ptr(), out.stride(0), C.c_void_p(_stream_ptr(out.device))))
+    return out
+
+
+def topk_select(score: torch.Tensor, seq_len: int, num_coming: int, start: int, important: int, recent: int,
+                keep_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """score [rows, >=seq_len] fp16/fp32 -> int32 [rows, keep_total] ascending kept token indices."""
+    lib = _lib.load()
+    _require_cuda(score, keep_idx)
+    plan = prune_plan(seq_len, num_coming, start, important, recent)
+    if plan is None:
+        raise ValueError("topk_select: cache already fits, nothing to select")
+    keep_total = plan[0]
+    if score.stride(-1) != 1:
+        score = score.contiguous()
+    rows = score.shape[0]
+    if keep_idx is None:
+        keep_idx = torch.empty((rows, keep_total), dtype=torch.int32, device=score.device)
+    a = _lib.SelectArgs()
+    a.struct_size = C.sizeof(_lib.SelectArgs)
+    a.num_rows, a.seq_len = rows, seq_len
+    a.num_coming, a.start, a.important, a.recent = num_coming, start, important, recent
+    a.score_dtype = _dtype_code(score)
+    a.score, a.score_stride = score.data_ptr(), score.stride(0)
+    a.keep_idx, a.keep_stride = keep_idx.data_ptr(), keep_idx.stride(0)
+    with torch.cuda.device(score.device):
+        _lib.check(lib.spatten_topk_select(C.byref(a), C.c_void_p(_stream_ptr(score.device))))
+    return keep_idx
+
+
+def kv_gather(k: torch.Tensor, v: torch.Tensor, keep_idx: torch.Tensor, k_out: Optional[torch.Tensor] = None,
+              v_out: Optional[torch.Tensor] = None, capacity: Optional[int] = None):
+    """K/V [b,H,S,D] (rows contiguous) -> [b,H,keep_total,D] gathered by keep_idx [H,keep_total].
+
+    k_out/v_out None: fresh tensors are returned, allocated with `capacity` rows per head (>= keep_total)
+    and sliced to keep_total, so later decode steps can append in place.  k_out is k: in-place compaction.
+    """
+    lib = _lib.load()
+    _require_cuda(k, v, keep_idx, k_out, v_out)
+    b, H, S, D = k.shape
+    keep_total = keep_idx.shape[1]
+    if keep_idx.dtype != torch.int32 or keep_idx.shape[0] != H:
+        raise ValueError("keep_idx must be int32 [H, keep_total]")
+    es = k.element_size()
+    for t in (k, v):
+        if t.stride(3) != 1 or t.stride(2) != D:
+            raise ValueError("kv_gather: K/V rows must be contiguous")
+    if k_out is None:
+        cap = max(keep_total, capacity or keep_total)
+        k_out = torch.empty((b, H, cap, D), dtype=k.dtype, device=k.device)[:, :, :keep_total]
+        v_out = torch.empty((b, H, cap, D), dtype=v.dtype, device=v.device)[:, :, :keep_total]
+    a = _lib.GatherArgs()
+    a.struct_size = C.sizeof(_lib.GatherArgs)
+    a.batch, a.num_heads, a.keep_total, a.row_bytes = b, H, keep_total, D * es
+    a.src_k, a.src_v = k.data_ptr(), v.data_ptr()
+    a.src_stride_b, a.src_stride_h = k.stride(0) * es, k.stride(1) * es
+    if v.stride() != k.stride() or v_out.stride() != k_out.stride():
+        raise ValueError("kv_gather: K and V must share strides")
+    a.dst_k, a.dst_v = k_out.data_ptr(), v_out.data_ptr()
+    a.dst_stride_b, a.dst_stride_h = k_out.stride(0) * es, k_out.stride(1) * es
+    a.keep_idx, a.keep_stride = keep_idx.data_ptr(), keep_idx.stride(0)
+    with torch.cuda.device(k.device):
+        _lib.check(lib.spatten_kv_gather(C.byref(a), C.c_void_p(_stream_ptr(k.device))))
+    return k_out, v_out

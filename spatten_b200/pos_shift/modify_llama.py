@@ -1,0 +1,160 @@
+"""Patched `LlamaAttention.forward` -- the B200 drop-in for the reference's
+`llama_pos_shift_attention_forward` (spatten_llm/pos_shift/modify_llama.py:31-168).
+
+Same signature, same return triple, same `self.attn_scores` side channel (:116-119), same shape
+ValueErrors (:121-131).  The projections stay `nn.Linear` (cuBLAS, as in the reference); everything
+between them -- RoPE(Q), KV append, RoPE(K at slot index), Q.K^T/sqrt(D), logit stash, mask, softmax,
+P.V -- is ONE launch of the CUDA library (`spatten_decode_attn`).  There is no eager fallback: a
+non-CUDA or non-fp16 input raises.
+
+The module is expected to expose the transformers-4.33 `LlamaAttention` attribute contract the
+reference reads: hidden_size, num_heads, num_key_value_heads, head_dim, config.pretraining_tp,
+q_proj/k_proj/v_proj/o_proj and (optionally) rotary_emb.base.
+"""
+from __future__ import annotations
+
+import types
+from typing import Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from .. import _lib, ops
+
+__all__ = ["enable_llama_pos_shift_attention", "llama_pos_shift_attention_forward"]
+
+_GROW = 256           # minimum spare rows when a cache buffer has to be (re)allocated
+
+
+def _capacity_view(t: torch.Tensor, D: int):
+    """If `t` [b,H,S,D] is a window onto a larger per-head buffer, return (full-capacity view, capacity)."""
+    b, H, S, _ = t.shape
+    if t.stride(3) != 1 or t.stride(2) != D or (b > 1 and t.stride(0) < H * t.stride(1)):
+        return None, 0
+    cap = t.stride(1) // D if H > 1 else (t.stride(0) // D if b > 1 else S)
+    if H == 1 and b == 1:
+        cap = (t.untyped_storage().nbytes() // t.element_size() - t.storage_offset()) // D
+    last = t.storage_offset() + (b - 1) * t.stride(0) + (H - 1) * t.stride(1) + cap * D
+    if cap < S or last * t.element_size() > t.untyped_storage().nbytes():
+        return None, 0
+    return t.as_strided((b, H, cap, D), t.stride(), t.storage_offset()), cap
+
+
+def _grow(past: Optional[torch.Tensor], b, H_kv, D, have, need, device):
+    """Buffer [b,H_kv,cap,D] holding the first `have` rows of `past`, cap >= need (amortised doubling)."""
+    if past is not None:
+        full, cap = _capacity_view(past, D)
+        if full is not None and cap >= need:
+            return full
+    cap = max(need + _GROW, 2 * have)
+    buf = torch.empty((b, H_kv, cap, D), dtype=torch.float16, device=device)
+    if past is not None and have:
+        buf[:, :, :have].copy_(past)
+    return buf
+
+
+def _rope_for(self, device, need: int) -> torch.Tensor:
+    tab = getattr(self, "_spatten_rope", None)
+    if tab is None or tab.shape[0] < need or tab.device != device:
+        base = float(getattr(getattr(self, "rotary_emb", None), "base", 10000.0))
+        n = max(need, 2048 if tab is None else 2 * tab.shape[0])
+        tab = ops.rope_table(self.head_dim, n, device, base)
+        self._spatten_rope = tab
+    return tab
+
+
+def llama_pos_shift_attention_forward(
+    self,
+    hidden_states: torch.Tensor,
+    attention_mask: Optional[torch.Tensor] = None,
+    position_ids: Optional[torch.LongTensor] = None,
+    past_key_value: Optional[Tuple[torch.Tensor]] = None,
+    output_attentions: bool = False,
+    use_cache: bool = False,
+    padding_mask: Optional[torch.Tensor] = None,
+) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[Tuple[torch.Tensor]]]:
+    if not hidden_states.is_cuda:
+        raise RuntimeError("spatten_b200: the patched forward runs on CUDA only (no CPU fallback)")
+    if hidden_states.dtype != torch.float16:
+        raise TypeError("spatten_b200: the CUDA path computes in fp16 (the reference GPU dtype, utils.py:62)")
+    _lib.load()
+    bsz, q_len, _ = hidden_states.size()
+    H, H_kv, D = self.num_heads, self.num_key_value_heads, self.head_dim
+    dev = hidden_states.device
+
+    # projections (:43-74).  pretraining_tp > 1 only re-associates the same matmuls (:43-69); the
+    # fused nn.Linear call is numerically the tp == 1 branch.
+    q = self.q_proj(hidden_states).view(bsz, q_len, H, D)
+    k_new = self.k_proj(hidden_states).view(bsz, q_len, H_kv, D)
+    v_new = self.v_proj(hidden_states).view(bsz, q_len, H_kv, D)
+
+    past_len = past_key_value[0].shape[-2] if past_key_value is not None else 0
+    kv_seq_len = past_len + q_len                                                    # :86-88
+    if position_ids is None:
+        position_ids = torch.arange(past_len, kv_seq_len, device=dev).unsqueeze(0).expand(bsz, q_len)
+    rope = _rope_for(self, dev, kv_seq_len)
+
+    mask = None
+    if attention_mask is not None:                                                   # :127-131
+        if attention_mask.size() != (bsz, 1, q_len, kv_seq_len):
+            raise ValueError(
+                f"Attention mask should be of size {(bsz, 1, q_len, kv_seq_len)}, but is {attention_mask.size()}")
+        mask = attention_mask.to(torch.float16).reshape(bsz, q_len, kv_seq_len).contiguous()
+
+    past_k = past_key_value[0] if past_key_value is not None else None
+    past_v = past_key_value[1] if past_key_value is not None else None
+    kbuf = _grow(past_k, bsz, H_kv, D, past_len, kv_seq_len, dev)
+    vbuf = _grow(past_v, bsz, H_kv, D, past_len, kv_seq_len, dev)
+    if vbuf.stride() != kbuf.stride():                     # keep K and V congruent for the kernel
+        vbuf2 = torch.empty_strided(kbuf.shape, kbuf.stride(), dtype=torch.float16, device=dev)
+        vbuf2[:, :, :past_len].copy_(vbuf[:, :, :past_len])
+        vbuf = vbuf2
+
+    if q_len == 1:
+        scores = torch.empty((bsz, H, 1, kv_seq_len), dtype=torch.float16, device=dev)
+        out = ops.decode_attn(q.view(bsz, H, D), kbuf, vbuf, past_len, rope,
+                              k_new=k_new.view(bsz, H_kv, D), v_new=v_new.view(bsz, H_kv, D),
+                              q_pos=position_ids.reshape(bsz), mask=mask,
+                              logits=scores.view(bsz, H, kv_seq_len),
+                              head_mask=getattr(self, "spatten_head_mask", None))
+    else:
+        # prefill / chunk: store the new K/V rows (:95-100), then score every query row against the cache
+        kbuf[:, :, past_len:kv_seq_len].copy_(k_new.transpose(1, 2))
+        vbuf[:, :, past_len:kv_seq_len].copy_(v_new.transpose(1, 2))
+        scores = torch.empty((bsz, H, q_len, kv_seq_len), dtype=torch.float16, device=dev)
+        out = ops.decode_attn(q, kbuf, vbuf, kv_seq_len, rope, q_pos=position_ids.reshape(bsz, q_len), mask=mask,
+                              logits=scores, head_mask=getattr(self, "spatten_head_mask", None))
+    self.attn_scores = scores                                                        # :116-119 (pre-mask logits)
+
+    attn_output = self.o_proj(out.view(bsz, q_len, H * D))                           # :146-163
+    attn_weights = None
+    if output_attentions:                                                            # :135-137, :165-166
+        s = scores if attention_mask is None else scores + attention_mask.to(torch.float16)
+        attn_weights = F.softmax(s, dim=-1, dtype=torch.float32).to(torch.float16)
+    present = (kbuf[:, :, :kv_seq_len], vbuf[:, :, :kv_seq_len]) if use_cache else None   # :100
+    return attn_output, attn_weights, present
+
+
+def _is_llama_attention(module) -> bool:
+    if getattr(module, "_spatten_llama_attention", False):
+        return True
+    try:
+        from transformers.models.llama.modeling_llama import LlamaAttention
+    except Exception:
+        return False
+    return isinstance(module, LlamaAttention)
+
+
+def enable_llama_pos_shift_attention(model) -> int:
+    """Rebind `.forward` of every LlamaAttention under `model` (reference :171-181).  Returns the count."""
+    n = 0
+    for module in model.modules():
+        if _is_llama_attention(module):
+            for attr in ("num_heads", "num_key_value_heads", "head_dim", "q_proj", "k_proj", "v_proj", "o_proj"):
+                if not hasattr(module, attr):
+                    raise AttributeError(
+                        f"{type(module).__name__} lacks `{attr}`: the patched forward needs the transformers-4.33 "
+                        "LlamaAttention contract the reference was written against (README.md:46)")
+            module.forward = types.MethodType(llama_pos_shift_attention_forward, module)
+            n += 1
+    return n

@@ -1,0 +1,94 @@
+"""CPU checks of the C-ABI boundary: the library loads, exports every symbol include/spatten_b200.h declares,
+struct layouts match the ctypes mirrors, and argument validation returns error codes (no GPU needed)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "spatten_b200.h")
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(spatten_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from spatten_b200 import _lib
+    lib = _lib.load()
+    names = _declared_functions()
+    assert len(names) >= 8
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/spatten_b200.h but not exported"
+
+
+def test_struct_layouts_match_c():
+    from spatten_b200 import _lib
+    prog = r'''
+    #include <stdio.h>
+    #include "spatten_b200.h"
+    int main(void) {
+      printf("%zu %zu %zu\n", sizeof(SpattenDecodeArgs), sizeof(SpattenSelectArgs), sizeof(SpattenGatherArgs));
+      return 0;
+    }'''
+    with tempfile.TemporaryDirectory() as td:
+        src, exe = os.path.join(td, "s.c"), os.path.join(td, "s")
+        open(src, "w").write(prog)
+        subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+        sizes = list(map(int, subprocess.check_output([exe]).split()))
+    assert sizes == [C.sizeof(_lib.DecodeArgs), C.sizeof(_lib.SelectArgs), C.sizeof(_lib.GatherArgs)]
+
+
+def test_argument_validation_without_gpu():
+    from spatten_b200 import _lib
+    lib = _lib.load()
+    assert lib.spatten_abi_version() == 1
+    a = _lib.DecodeArgs()
+    assert lib.spatten_decode_attn(C.byref(a), None) == -1 and b"struct_size" in lib.spatten_last_error()
+    a.struct_size = C.sizeof(a)
+    a.batch, a.num_heads, a.num_kv_heads, a.head_dim, a.kv_len = 1, 4, 4, 80, 8
+    assert lib.spatten_decode_attn(C.byref(a), None) == -2            # head_dim unsupported
+    assert lib.spatten_decode_attn(None, None) == -1
+    s = _lib.SelectArgs()
+    assert lib.spatten_topk_select(C.byref(s), None) == -1
+    g = _lib.GatherArgs()
+    assert lib.spatten_kv_gather(C.byref(g), None) == -1
+    kt, wb, we = C.c_int32(), C.c_int32(), C.c_int32()
+    assert lib.spatten_prune_plan(128, 0, 4, 30, 30, C.byref(kt), C.byref(wb), C.byref(we)) == 0
+    assert (kt.value, wb.value, we.value) == (64, 4, 98)
+    assert lib.spatten_prune_plan(60, 0, 4, 30, 30, None, None, None) == 1
+    assert lib.spatten_prune_plan(40, 0, 2, 0, 4, None, None, None) == -1
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from spatten_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libspatten_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_product_package_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "spatten_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                assert "oracle" not in open(os.path.join(dp, f)).read().replace("the oracle", "").replace(
+                    "pinned oracle", ""), f"{f} references the oracle"
+
+
+def test_capacity_view_logic_cpu():
+    import torch
+    from spatten_b200.pos_shift.modify_llama import _capacity_view
+    buf = torch.zeros(2, 3, 50, 8, dtype=torch.float16)
+    full, cap = _capacity_view(buf[:, :, :20], 8)
+    assert cap == 50 and full.shape == (2, 3, 50, 8) and full.data_ptr() == buf.data_ptr()
+    plain = torch.zeros(2, 3, 20, 8, dtype=torch.float16)
+    full, cap = _capacity_view(plain, 8)
+    assert cap == 20
+    assert _capacity_view(plain.transpose(1, 2), 8) == (None, 0)
