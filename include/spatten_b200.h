@@ -109,6 +109,14 @@ typedef struct SpattenDecodeArgs {
 size_t spatten_decode_workspace_bytes(int32_t batch, int32_t num_heads, int32_t head_dim);
 int spatten_decode_attn(const SpattenDecodeArgs* args, void* stream);
 
+/* The same step with HOST buffers for the per-step tensors (what a caller that lives on the CPU side of an
+ * FFI hands over): q_host / k_new_host / v_new_host are copied into the device staging buffers args->q /
+ * args->k_new / args->v_new, the kernel runs, args->out is copied to out_host and the stream is
+ * synchronised before returning.  The KV cache, RoPE table and workspace stay resident on the device (they
+ * are state, like the reference's past_key_values).  Pinned host memory makes the copies asynchronous. */
+int spatten_decode_attn_host(const SpattenDecodeArgs* args, const void* q_host, const void* k_new_host,
+                             const void* v_new_host, void* out_host, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * KV-cache token pruning.  Replaces SpAttenKVCache.apply_token_pruning
  * (spatten_llm/kv_cache_token_pruning.py:42-96) with three device-side steps and no host sync

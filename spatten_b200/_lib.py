@@ -86,6 +86,8 @@ def load() -> C.CDLL:
     lib.spatten_decode_workspace_bytes.restype = C.c_size_t
     lib.spatten_decode_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     lib.spatten_decode_attn.argtypes = [C.POINTER(DecodeArgs), C.c_void_p]
+    lib.spatten_decode_attn_host.argtypes = [C.POINTER(DecodeArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p]
     _bind_optional(lib)
     if lib.spatten_abi_version() != 1:
         raise RuntimeError(f"spatten_b200: ABI version {lib.spatten_abi_version()} != 1")

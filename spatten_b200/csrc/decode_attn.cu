@@ -689,3 +689,27 @@ extern "C" int spatten_decode_attn(const SpattenDecodeArgs* a, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return a->head_dim == 128 ? launch_decode<128>(p, st) : launch_decode<64>(p, st);
 }
+
+// Same call with HOST buffers for the per-step tensors: copies q / k_new / v_new from (pinned) host memory into
+// the device staging buffers named by `args`, launches, copies `out` back and synchronises the stream.
+extern "C" int spatten_decode_attn_host(const SpattenDecodeArgs* a, const void* q_host, const void* k_new_host,
+                                        const void* v_new_host, void* out_host, void* stream) {
+  SPATTEN_CHECK_ARG(a != nullptr && a->struct_size == sizeof(SpattenDecodeArgs), "spatten_decode_attn_host: bad args");
+  SPATTEN_CHECK_ARG(q_host && out_host && a->q && a->out, "spatten_decode_attn_host: NULL q/out");
+  SPATTEN_CHECK_ARG(!a->append || (k_new_host && v_new_host && a->k_new && a->v_new),
+                    "spatten_decode_attn_host: append needs k_new/v_new host and staging buffers");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int q_len = a->q_len > 1 ? a->q_len : 1;
+  const size_t qb = static_cast<size_t>(a->batch) * q_len * a->num_heads * a->head_dim * sizeof(__half);
+  const size_t kb = static_cast<size_t>(a->batch) * a->num_kv_heads * a->head_dim * sizeof(__half);
+  cudaError_t e = cudaMemcpyAsync(const_cast<void*>(a->q), q_host, qb, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && a->append) e = cudaMemcpyAsync(const_cast<void*>(a->k_new), k_new_host, kb, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && a->append) e = cudaMemcpyAsync(const_cast<void*>(a->v_new), v_new_host, kb, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return cuda_fail(e, "spatten_decode_attn_host: H2D copy");
+  const int rc = spatten_decode_attn(a, stream);
+  if (rc != SPATTEN_OK) return rc;
+  e = cudaMemcpyAsync(out_host, a->out, qb, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cuda_fail(e, "spatten_decode_attn_host: D2H copy / sync");
+  return SPATTEN_OK;
+}

@@ -46,22 +46,18 @@ def rope_table(head_dim: int, length: int, device, base: float = 10000.0) -> tor
     return tab.to(device).contiguous()
 
 
-def decode_attn(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, kv_len: int, rope: torch.Tensor,
-                k_new: Optional[torch.Tensor] = None, v_new: Optional[torch.Tensor] = None,
-                q_pos: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
-                head_mask: Optional[torch.Tensor] = None, logits: Optional[torch.Tensor] = None,
-                importance: Optional[torch.Tensor] = None, head_importance: Optional[torch.Tensor] = None,
-                out: Optional[torch.Tensor] = None, flags: int = 0) -> torch.Tensor:
-    """Attention of new-token queries against the KV cache -- `spatten_decode_attn`.
+def make_decode_args(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, kv_len: int, rope: torch.Tensor,
+                     k_new: Optional[torch.Tensor] = None, v_new: Optional[torch.Tensor] = None,
+                     q_pos: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
+                     head_mask: Optional[torch.Tensor] = None, logits: Optional[torch.Tensor] = None,
+                     importance: Optional[torch.Tensor] = None, head_importance: Optional[torch.Tensor] = None,
+                     out: Optional[torch.Tensor] = None, flags: int = 0):
+    """Validate tensors and fill a `SpattenDecodeArgs`.  Returns (args, out, keepalive).
 
-    q: fp16 [b,H,D] (decode) or [b,q_len,H,D] (prefill rows; the new K/V must already be in the cache
-    and k_new must be None); k_cache/v_cache [b,H_kv,cap,D] fp16 (any batch/head strides, rows
-    contiguous); kv_len tokens valid; k_new/v_new [b,H_kv,D] appended at slot kv_len when given.
-    q_pos int64 [b] / [b,q_len]; mask fp16 [b,n] / [b,q_len,n] additive.
-    Returns out fp16 with q's shape.  `logits` receives attn_scores: [b,H,>=n] (decode) or
-    [b,H,q_len,>=n]; `importance` fp32 [b,H,>=n] and `head_importance` fp32 [H] accumulate in place.
+    Callers that launch the same step repeatedly (bench, CUDA-graph capture) build the struct once and
+    call `lib.spatten_decode_attn(byref(args), stream)` directly.
     """
-    lib = _lib.load()
+    _lib.load()
     _require_cuda(q, k_cache, v_cache, rope, k_new, v_new, q_pos, mask, head_mask, logits, importance,
                   head_importance, out)
     if q.dim() == 3:
@@ -117,8 +113,25 @@ def decode_attn(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, k
         a.head_importance = head_importance.data_ptr()
     ws = decode_workspace(q.device, b * q_len, H, D)
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    keep = (q, k_new, v_new, q_pos, mask, ws)      # tensors the struct points at but the caller may not hold
+    return a, out, keep
+
+
+def decode_attn(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, kv_len: int, rope: torch.Tensor,
+                **kw) -> torch.Tensor:
+    """Attention of new-token queries against the KV cache -- `spatten_decode_attn`.
+
+    q: fp16 [b,H,D] (decode) or [b,q_len,H,D] (prefill rows; the new K/V must already be in the cache
+    and k_new must be None); k_cache/v_cache [b,H_kv,cap,D] fp16 (any batch/head strides, rows
+    contiguous); kv_len tokens valid; k_new/v_new [b,H_kv,D] appended at slot kv_len when given.
+    q_pos int64 [b] / [b,q_len]; mask fp16 [b,n] / [b,q_len,n] additive.
+    Returns out fp16 with q's shape.  `logits` receives attn_scores: [b,H,>=n] (decode) or
+    [b,H,q_len,>=n]; `importance` fp32 [b,H,>=n] and `head_importance` fp32 [H] accumulate in place.
+    Keyword arguments as in `make_decode_args`.
+    """
+    a, out, _keep = make_decode_args(q, k_cache, v_cache, kv_len, rope, **kw)
     with torch.cuda.device(q.device):
-        _lib.check(lib.spatten_decode_attn(C.byref(a), C.c_void_p(_stream_ptr(q.device))))
+        _lib.check(_lib.load().spatten_decode_attn(C.byref(a), C.c_void_p(_stream_ptr(q.device))))
     return out
 
 
