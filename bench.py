@@ -183,6 +183,8 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 
 def run_ours(args):
+    import faulthandler
+    faulthandler.dump_traceback_later(150, exit=True)      # a wedged collective must not eat the GPU lease
     import torch
     import torch.distributed as dist
     from spatten_b200 import _lib, ops
@@ -271,13 +273,19 @@ def run_ours(args):
 
     def timed(run, steps, warmup, min_warm_s=0.0):
         with torch.cuda.stream(stream):
+            # at least `warmup` untimed steps, and long enough under load for the clock sampler to see it.
+            # The count must be identical on every rank (each step contains collectives).
             t_w = time.perf_counter()
-            done = 0
-            # at least `warmup` untimed steps, and long enough under load for the clock sampler to see it
-            while done < warmup or (time.perf_counter() - t_w) < min_warm_s:
+            for _ in range(warmup):
                 run()
-                done += 1
-                if done % 64 == 0:
+            stream.synchronize()
+            est = torch.tensor([(time.perf_counter() - t_w) / warmup], device=dev)
+            if world > 1:
+                dist.all_reduce(est, op=dist.ReduceOp.MAX)
+            extra = int(min(20000, max(0.0, min_warm_s) / max(float(est.item()), 1e-6)))
+            for i in range(extra):
+                run()
+                if i % 64 == 63:
                     stream.synchronize()
             stream.synchronize()
             if world > 1:
@@ -309,7 +317,7 @@ def run_ours(args):
     if sampler:
         sampler.start()
         time.sleep(0.3)
-    total_ms = timed(run_full, args.steps, max(3, args.warmup), min_warm_s=0.6)
+    total_ms = timed(run_full, args.steps, max(3, args.warmup), min_warm_s=args.min_warm_s)
     ms_per_step = total_ms / args.steps
     value = b / (ms_per_step * 1e-3)
 
@@ -431,7 +439,13 @@ def run_ours(args):
         line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tearing the process group down while captured NCCL work is still referenced by a CUDA graph hangs
+        # (seen on this pool: destroy_process_group never returns).  Everything is printed; leave hard.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
@@ -442,6 +456,8 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--collective", choices=["allreduce", "allgather"], default="allreduce")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--min-warm-s", type=float, default=0.6,
+                    help="keep warming up until this many seconds have run under load (clock sampling); 0 under ncu")
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
