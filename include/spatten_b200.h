@@ -60,6 +60,8 @@ int spatten_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * a decoder: a layer's cache was last written one whole decode step earlier).  The kernel then streams the
  * first K/V tiles into shared memory BEFORE waiting for its predecessor, hiding launch + HBM latency. */
 #define SPATTEN_DECODE_PDL_KV_STABLE 2u
+/* Never use the thread-block-cluster (DSMEM merge) variant; always global partials + tickets. */
+#define SPATTEN_DECODE_NO_CLUSTER 4u
 
 typedef struct SpattenDecodeArgs {
   uint32_t struct_size;   /* = sizeof(SpattenDecodeArgs), ABI guard */

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libspatten_b200.so")
 SPATTEN_OK = 0
 DECODE_PDL = 1
 DECODE_PDL_KV_STABLE = 2
+DECODE_NO_CLUSTER = 4
 ERR_NAMES = {-1: "SPATTEN_ERR_INVALID", -2: "SPATTEN_ERR_UNSUPPORTED", -3: "SPATTEN_ERR_CUDA",
              -4: "SPATTEN_ERR_WORKSPACE"}
 

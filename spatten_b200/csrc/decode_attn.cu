@@ -36,6 +36,7 @@ constexpr int kTile = 4 * kPasses;  // tokens per pipeline stage (per warp)
 constexpr int kStages = 3;    // ring depth per warp -> 8 warps * 3 * 8 KiB = 192 KiB in flight per SM (D=128)
 constexpr int kMaxPartials = 8192;  // (row, split) partial records the workspace holds
 constexpr int kMaxSplits = 256;     // splits per row the merge handles
+constexpr int kMaxClusterSize = 8;  // CTAs per cluster in cluster mode: 8 (portable maximum) or 4
 constexpr size_t kTicketBytes = static_cast<size_t>(kMaxPartials) * sizeof(unsigned int);  // per-row tickets
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -65,6 +66,9 @@ struct DecodeParams {
   int rows, rpc, spc, n_rg, n_ranges, n_splits, tok_per_split;
   float sqrt_d, rsqrt_d;
   int pdl;                 // launched with programmatic stream serialization (SPATTEN_DECODE_PDL)
+  int ds_shift;            // cluster mode: log2(D * rpc / cluster)
+  int cluster;             // 0: global partials + per-row tickets; 4 or 8: every split of a row lives in one
+                           // thread-block cluster of that size and partials are merged through distributed shared memory
   unsigned long long* dbg;  // optional [grid][8 warps][8] globaltimer stamps (tools/microbench.py --timeline)
 };
 
@@ -73,10 +77,15 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-#define STAMP(k)                                                                                   \
-  do {                                                                                             \
-    if (p.dbg && lane == 0) p.dbg[(static_cast<size_t>(blockIdx.x) * kWarps + warp) * 8 + (k)] = gtime(); \
-  } while (0)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store a float into the shared memory of CTA `cta` of this cluster (same layout in every CTA)
+__device__ __forceinline__ void st_dsmem(float* local, unsigned cta, float v) {
+  unsigned raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(local)), "r"(cta));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(v) : "memory");
+}
 
 template <int N>
 struct HalfVec {
@@ -93,7 +102,7 @@ __device__ __forceinline__ float div_by_const(float x, float c, float rc) {
   return (fabsf(y2) <= 3.4028234e38f) ? y2 : y;
 }
 
-template <int D>
+template <int D, int MODE, bool DBG>   // MODE 0: global partials + tickets (or one split); MODE 1: cluster / DSMEM merge
 __global__ void __launch_bounds__(kThreads, 1) decode_attn_kernel(const DecodeParams p) {
   constexpr int E2 = D / 16;   // halves per lane in each half of the row (8 lanes cover D/2)
   constexpr int NH2 = E2 / 2;  // half2 per lane per half-row
@@ -103,6 +112,10 @@ __global__ void __launch_bounds__(kThreads, 1) decode_attn_kernel(const DecodePa
   constexpr int kRowBytes = D * 2;
   constexpr int kTileBytes = kTile * kRowBytes;
   constexpr int kWarpSmem = kStages * 2 * kTileBytes;
+#define STAMP(k)                                                                                             \
+  do {                                                                                                       \
+    if (DBG && p.dbg && lane == 0) p.dbg[(static_cast<size_t>(blockIdx.x) * kWarps + warp) * 8 + (k)] = gtime(); \
+  } while (0)
 
   extern __shared__ __align__(128) uint8_t smem[];
 
@@ -117,8 +130,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_attn_kernel(const DecodePa
   // kernel still in flight, wait for the previous kernel right here.
   if (p.pdl != 2) asm volatile("griddepcontrol.wait;" ::: "memory");
 
-  const int rg = blockIdx.x % p.n_rg;
-  const int range = blockIdx.x / p.n_rg;
+  // MODE 0: blockIdx = range * n_rg + row group.   MODE 1: blockIdx = cluster (= row group) * cluster size + CTA rank.
+  const int rg = MODE ? blockIdx.x / p.cluster : blockIdx.x % p.n_rg;
+  const int range = MODE ? blockIdx.x % p.cluster : blockIdx.x / p.n_rg;
   const int row = rg * p.rpc + (warp % p.rpc);
   const int split = range * p.spc + warp / p.rpc;
   const bool row_ok = row < p.rows;
@@ -128,19 +142,22 @@ __global__ void __launch_bounds__(kThreads, 1) decode_attn_kernel(const DecodePa
   const int kvh = h / p.n_rep;
   const bool live = row_ok && (p.head_mask == nullptr || p.head_mask[h] != 0);
 
+  // the cached tokens are cut into n_splits ranges of tok_per_split; the appended token rides with the last one
   int t0 = split * p.tok_per_split;
-  int t1 = min(t0 + p.tok_per_split, p.n_total);
-  if (!live || t0 >= t1) { t0 = 0; t1 = 0; }
-  const int t1c = min(t1, p.kv_len);                         // cached part of the range
-  const bool owns_new = live && p.append && t1 == p.n_total && t1 > t0;  // slot kv_len is ours
-  const int nt = t1c > t0 ? (t1c - t0 + kTile - 1) / kTile : 0;
+  int t1c = min(t0 + p.tok_per_split, p.kv_len);
+  if (!live || t0 >= t1c) { t0 = 0; t1c = 0; }
+  const int last_split = p.kv_len > 0 ? (p.kv_len - 1) / p.tok_per_split : 0;
+  const bool owns_new = live && p.append && split == last_split;   // token index kv_len (== t1c) is ours
+  if (owns_new && t1c == 0) t0 = p.kv_len;                         // kv_len == 0: the range is just the new token
+  const int t_end = owns_new ? p.kv_len + 1 : t1c;
+  const int nt = t_end > t0 ? (t_end - t0 + kTile - 1) / kTile : 0;
   STAMP(0);
 
   const __half* Kc = p.k_cache + bi * p.stride_b + kvh * p.stride_h;
   const __half* Vc = p.v_cache + bi * p.stride_b + kvh * p.stride_h;
 
   // RoPE rows of one tile: cos | sin for the 4 passes of this lane's key group.  Rows are shared by all
-  // heads, so the other warps of the CTA (same token range) hit L1.
+  // heads, so the other warps of the CTA that work on the same token range hit L1.
   auto load_table = [&](int tok0, HV (&cs)[kPasses], HV (&sn)[kPasses]) {
 #pragma unroll
     for (int ps = 0; ps < kPasses; ++ps) {
@@ -171,7 +188,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_attn_kernel(const DecodePa
   auto issue = [&](int i) {
     const int s = i % kStages;
     const int tok = t0 + i * kTile;
-    const uint32_t bytes = static_cast<uint32_t>(min(kTile, t1c - tok)) * kRowBytes;
+    const int ncopy = min(kTile, t1c - tok);            // rows that come from the cache (the new token does not)
+    if (ncopy <= 0) return;
+    const uint32_t bytes = static_cast<uint32_t>(ncopy) * kRowBytes;
     mbar_expect_tx(&bars[s], 2 * bytes);
     bulk_g2s(wsm + s * 2 * kTileBytes, Kc + static_cast<int64_t>(tok) * D, bytes, &bars[s], pol);
     bulk_g2s(wsm + s * 2 * kTileBytes + kTileBytes, Vc + static_cast<int64_t>(tok) * D, bytes, &bars[s], pol);
@@ -180,6 +199,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_attn_kernel(const DecodePa
 #pragma unroll
     for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
     fence_mbar_init();
+#pragma unroll 1
     for (int i = 0; i < min(nt, kStages); ++i) issue(i);
   }
   __syncwarp();
@@ -206,74 +226,17 @@ __global__ void __launch_bounds__(kThreads, 1) decode_attn_kernel(const DecodePa
 #pragma unroll
   for (int i = 0; i < E2; ++i) accl[i] = acch[i] = 0.f;
 
-  // this lane's 2*E2 terms of q . rope(k): rotated key rounded to fp16 after every elementwise op (:27),
-  // products summed in fp32 (two chains for ILP); the 8 lanes of the key group are summed by the caller
-  auto rot_dot = [&](const HV& kl, const HV& kh, const HV& c_, const HV& s_) -> float {
-    float d0 = 0.f, d1 = 0.f;
-#pragma unroll
-    for (int i = 0; i < NH2; ++i) {
-      const __half2 rl = __hsub2_rn(__hmul2_rn(kl.h[i], c_.h[i]), __hmul2_rn(kh.h[i], s_.h[i]));
-      const __half2 rh = __hadd2_rn(__hmul2_rn(kh.h[i], c_.h[i]), __hmul2_rn(kl.h[i], s_.h[i]));
-      const float2 fl = __half22float2(rl), fh = __half22float2(rh);
-      d0 = fmaf(ql[2 * i], fl.x, d0);
-      d0 = fmaf(ql[2 * i + 1], fl.y, d0);
-      d1 = fmaf(qh[2 * i], fh.x, d1);
-      d1 = fmaf(qh[2 * i + 1], fh.y, d1);
-    }
-    return d0 + d1;
-  };
-  // fp16 logit exactly as the reference forms it: fp16(matmul) / sqrt(D) -> fp16 (:111-113)
-  auto to_logit = [&](float d) -> __half {
-    return __float2half_rn(div_by_const(__half2float(__float2half_rn(d)), p.sqrt_d, p.rsqrt_d));
-  };
-  auto pv = [&](const HV& vl, const HV& vh, float pr) {
-#pragma unroll
-    for (int i = 0; i < NH2; ++i) {
-      const float2 fl = __half22float2(vl.h[i]), fh = __half22float2(vh.h[i]);
-      accl[2 * i] = fmaf(pr, fl.x, accl[2 * i]);
-      accl[2 * i + 1] = fmaf(pr, fl.y, accl[2 * i + 1]);
-      acch[2 * i] = fmaf(pr, fh.x, acch[2 * i]);
-      acch[2 * i + 1] = fmaf(pr, fh.y, acch[2 * i + 1]);
-    }
-  };
   __half* lg = p.logits ? p.logits + bi * p.logits_stride_b + h * p.logits_stride + (bq % p.q_len) * p.logits_stride_q
                         : nullptr;
   const __half* mk = p.mask ? p.mask + static_cast<int64_t>(bq) * p.n_total : nullptr;
 
-  // online softmax over kPasses scores per lane (one per key group); m, corr are warp-uniform
-  auto online_update = [&](const float (&sc)[kPasses], float (&pr)[kPasses]) {
-    float mx = sc[0];
-#pragma unroll
-    for (int ps = 1; ps < kPasses; ++ps) mx = fmaxf(mx, sc[ps]);
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
-    const float m_new = fmaxf(m, mx);
-    if (m_new == -CUDART_INF_F) {             // nothing valid yet
-#pragma unroll
-      for (int ps = 0; ps < kPasses; ++ps) pr[ps] = 0.f;
-      return;
-    }
-    float psum = 0.f;
-#pragma unroll
-    for (int ps = 0; ps < kPasses; ++ps) {
-      pr[ps] = fast_exp2((sc[ps] - m_new) * kLog2e);
-      psum += pr[ps];
-    }
-    if (m_new != m) {                         // warp-uniform: rescale only when the running max moved
-      const float corr = fast_exp2((m - m_new) * kLog2e);
-      l *= corr;
-#pragma unroll
-      for (int i = 0; i < E2; ++i) { accl[i] *= corr; acch[i] *= corr; }
-      m = m_new;
-    }
-    l += psum;
-  };
-
-  // ---- stream the cached tokens --------------------------------------------------------------------
+  // ---- stream the tokens of the range ---------------------------------------------------------------------
+#pragma unroll 1
   for (int i = 0; i < nt; ++i) {
     const int s = i % kStages;
     const int tok0 = t0 + i * kTile;
-    const int ntok = min(kTile, t1c - tok0);
+    const int ntok = min(kTile, t_end - tok0);          // valid tokens of the tile (incl. the appended one)
+    const int ncopy = max(0, min(kTile, t1c - tok0));   // of which this many were bulk-copied from the cache
     uint8_t* Ks = wsm + s * 2 * kTileBytes;
     uint8_t* Vs = Ks + kTileBytes;
 
@@ -281,17 +244,37 @@ __global__ void __launch_bounds__(kThreads, 1) decode_attn_kernel(const DecodePa
     HV csn[kPasses], snn[kPasses];
     if (i + 1 < nt) load_table(tok0 + kTile, csn, snn);
 
-    if (ntok < kTile) {
-      // zero the rows the partial copy does not write, so masked lanes multiply finite numbers
-      for (int o = ntok * kRowBytes + lane * 16; o < kTileBytes; o += 32 * 16) {
+    if (ntok < kTile || ncopy < ntok) {
+      // zero the rows the copy does not write, so masked lanes multiply finite numbers
+#pragma unroll 1
+      for (int o = ncopy * kRowBytes + lane * 16; o < kTileBytes; o += 32 * 16) {
         *reinterpret_cast<uint4*>(Ks + o) = make_uint4(0, 0, 0, 0);
         *reinterpret_cast<uint4*>(Vs + o) = make_uint4(0, 0, 0, 0);
       }
       __syncwarp();
     }
-    mbar_wait(&bars[s], (i / kStages) & 1);
+    if (ncopy > 0) mbar_wait(&bars[s], (i / kStages) & 1);
     if (i == 0) STAMP(2);   // first tile landed
+    if (ncopy < ntok) {
+      // the appended token (modify_llama.py:95-100): its un-rotated K/V row goes into the tile and into slot kv_len
+      constexpr int kChunks = kRowBytes / 16;           // 16-byte chunks per row: 16 (D=128) or 8 (D=64)
+      const int r = p.kv_len - tok0;
+      const int which = lane / kChunks, ch = lane % kChunks;   // D=128: lanes 0-15 copy K, 16-31 copy V
+#pragma unroll 1
+      for (int w = which; w < 2; w += 32 / kChunks) {
+        const __half* src = (w ? p.v_new : p.k_new) + (static_cast<int64_t>(bi) * p.H_kv + kvh) * D + ch * 8;
+        const uint4 val = *reinterpret_cast<const uint4*>(src);
+        *reinterpret_cast<uint4*>((w ? Vs : Ks) + r * kRowBytes + ch * 16) = val;
+        if ((h % p.n_rep) == 0) {                        // one writer per kv head
+          __half* dst = (w ? p.v_cache : p.k_cache) + bi * p.stride_b + kvh * p.stride_h +
+                        static_cast<int64_t>(p.kv_len) * D + ch * 8;
+          *reinterpret_cast<uint4*>(dst) = val;
+        }
+      }
+      __syncwarp();
+    }
 
+    // scores of the tile: rotated key rounded to fp16 after every elementwise op (:27), products summed in fp32
     float d[kPasses];
 #pragma unroll
     for (int ps = 0; ps < kPasses; ++ps) {
@@ -299,32 +282,71 @@ __global__ void __launch_bounds__(kThreads, 1) decode_attn_kernel(const DecodePa
       HV kl, kh;
       *reinterpret_cast<Vec*>(&kl) = *reinterpret_cast<const Vec*>(Ks + tl * kRowBytes + c * VB);
       *reinterpret_cast<Vec*>(&kh) = *reinterpret_cast<const Vec*>(Ks + tl * kRowBytes + D + c * VB);
-      d[ps] = rot_dot(kl, kh, cs[ps], sn[ps]);
+      float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+      for (int e = 0; e < NH2; ++e) {
+        const __half2 rl = __hsub2_rn(__hmul2_rn(kl.h[e], cs[ps].h[e]), __hmul2_rn(kh.h[e], sn[ps].h[e]));
+        const __half2 rh = __hadd2_rn(__hmul2_rn(kh.h[e], cs[ps].h[e]), __hmul2_rn(kl.h[e], sn[ps].h[e]));
+        const float2 fl = __half22float2(rl), fh = __half22float2(rh);
+        d0 = fmaf(ql[2 * e], fl.x, d0);
+        d0 = fmaf(ql[2 * e + 1], fl.y, d0);
+        d1 = fmaf(qh[2 * e], fh.x, d1);
+        d1 = fmaf(qh[2 * e + 1], fh.y, d1);
+      }
+      d[ps] = d0 + d1;
     }
 #pragma unroll
     for (int o = 1; o <= 4; o <<= 1) {
 #pragma unroll
       for (int ps = 0; ps < kPasses; ++ps) d[ps] += __shfl_xor_sync(0xffffffffu, d[ps], o);
     }
+    // fp16 logit exactly as the reference forms it: fp16(matmul) / sqrt(D) -> fp16 (:111-113); mask (:132)
     float sc[kPasses], pr[kPasses];
+    float mx = -CUDART_INF_F;
 #pragma unroll
     for (int ps = 0; ps < kPasses; ++ps) {
       const int tl = ps * 4 + g;
       const int j = tok0 + tl;
       const bool valid = tl < ntok;
-      __half s16 = to_logit(d[ps]);
+      __half s16 = __float2half_rn(div_by_const(__half2float(__float2half_rn(d[ps])), p.sqrt_d, p.rsqrt_d));
       if (valid && c == 0 && lg) lg[j] = s16;
       if (mk && valid) s16 = __hadd_rn(s16, mk[j]);
       sc[ps] = valid ? __half2float(s16) : -CUDART_INF_F;
+      mx = fmaxf(mx, sc[ps]);
     }
-    online_update(sc, pr);
+    // online softmax (:135): m is warp-uniform; l and acc are per key group until the end
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+    const float m_new = fmaxf(m, mx);
+    if (m_new > -CUDART_INF_F) {
+      if (m_new != m) {                         // warp-uniform: rescale only when the running max moved
+        const float corr = fast_exp2((m - m_new) * kLog2e);
+        l *= corr;
 #pragma unroll
-    for (int ps = 0; ps < kPasses; ++ps) {
-      const int tl = ps * 4 + g;
-      HV vl, vh;
-      *reinterpret_cast<Vec*>(&vl) = *reinterpret_cast<const Vec*>(Vs + tl * kRowBytes + c * VB);
-      *reinterpret_cast<Vec*>(&vh) = *reinterpret_cast<const Vec*>(Vs + tl * kRowBytes + D + c * VB);
-      pv(vl, vh, pr[ps]);
+        for (int e = 0; e < E2; ++e) { accl[e] *= corr; acch[e] *= corr; }
+        m = m_new;
+      }
+#pragma unroll
+      for (int ps = 0; ps < kPasses; ++ps) {
+        pr[ps] = fast_exp2((sc[ps] - m) * kLog2e);
+        l += pr[ps];
+      }
+      // P.V (:138)
+#pragma unroll
+      for (int ps = 0; ps < kPasses; ++ps) {
+        const int tl = ps * 4 + g;
+        HV vl, vh;
+        *reinterpret_cast<Vec*>(&vl) = *reinterpret_cast<const Vec*>(Vs + tl * kRowBytes + c * VB);
+        *reinterpret_cast<Vec*>(&vh) = *reinterpret_cast<const Vec*>(Vs + tl * kRowBytes + D + c * VB);
+#pragma unroll
+        for (int e = 0; e < NH2; ++e) {
+          const float2 fl = __half22float2(vl.h[e]), fh = __half22float2(vh.h[e]);
+          accl[2 * e] = fmaf(pr[ps], fl.x, accl[2 * e]);
+          accl[2 * e + 1] = fmaf(pr[ps], fl.y, accl[2 * e + 1]);
+          acch[2 * e] = fmaf(pr[ps], fh.x, acch[2 * e]);
+          acch[2 * e + 1] = fmaf(pr[ps], fh.y, acch[2 * e + 1]);
+        }
+      }
     }
 
     __syncwarp();                                  // every lane is done reading stage s
@@ -333,43 +355,6 @@ __global__ void __launch_bounds__(kThreads, 1) decode_attn_kernel(const DecodePa
     for (int ps = 0; ps < kPasses; ++ps) { cs[ps] = csn[ps]; sn[ps] = snn[ps]; }
   }
   STAMP(3);   // streaming loop done
-
-  // ---- the appended token: read from k_new / v_new, store into slot kv_len (modify_llama.py:95-100) ---
-  if (owns_new) {
-    const int j = p.kv_len;
-    const __half* kn = p.k_new + (static_cast<int64_t>(bi) * p.H_kv + kvh) * D;
-    const __half* vn = p.v_new + (static_cast<int64_t>(bi) * p.H_kv + kvh) * D;
-    HV kl, kh, vl, vh, c1, s1;
-    *reinterpret_cast<Vec*>(&kl) = *reinterpret_cast<const Vec*>(kn + c * E2);
-    *reinterpret_cast<Vec*>(&kh) = *reinterpret_cast<const Vec*>(kn + D / 2 + c * E2);
-    *reinterpret_cast<Vec*>(&vl) = *reinterpret_cast<const Vec*>(vn + c * E2);
-    *reinterpret_cast<Vec*>(&vh) = *reinterpret_cast<const Vec*>(vn + D / 2 + c * E2);
-    const int jr = min(j, p.rope_len - 1);
-    *reinterpret_cast<Vec*>(&c1) = __ldg(reinterpret_cast<const Vec*>(p.rope + static_cast<int64_t>(jr) * D + c * E2));
-    *reinterpret_cast<Vec*>(&s1) =
-        __ldg(reinterpret_cast<const Vec*>(p.rope + static_cast<int64_t>(jr) * D + D / 2 + c * E2));
-    if (g == 0 && (h % p.n_rep) == 0) {            // one writer per kv head
-      __half* kd = p.k_cache + bi * p.stride_b + kvh * p.stride_h + static_cast<int64_t>(j) * D;
-      __half* vd = p.v_cache + bi * p.stride_b + kvh * p.stride_h + static_cast<int64_t>(j) * D;
-      *reinterpret_cast<Vec*>(kd + c * E2) = *reinterpret_cast<Vec*>(&kl);
-      *reinterpret_cast<Vec*>(kd + D / 2 + c * E2) = *reinterpret_cast<Vec*>(&kh);
-      *reinterpret_cast<Vec*>(vd + c * E2) = *reinterpret_cast<Vec*>(&vl);
-      *reinterpret_cast<Vec*>(vd + D / 2 + c * E2) = *reinterpret_cast<Vec*>(&vh);
-    }
-    float d = rot_dot(kl, kh, c1, s1);
-    d += __shfl_xor_sync(0xffffffffu, d, 1);
-    d += __shfl_xor_sync(0xffffffffu, d, 2);
-    d += __shfl_xor_sync(0xffffffffu, d, 4);
-    __half s16 = to_logit(d);
-    if (lane == 0 && lg) lg[j] = s16;
-    if (mk) s16 = __hadd_rn(s16, mk[j]);
-    float sc[kPasses], pr[kPasses];
-#pragma unroll
-    for (int ps = 0; ps < kPasses; ++ps) sc[ps] = -CUDART_INF_F;
-    if (g == 0) sc[0] = __half2float(s16);          // count it once (key group 0)
-    online_update(sc, pr);
-    pv(vl, vh, pr[0]);
-  }
 
   // ---- merge the 4 key groups of the warp -------------------------------------------------------------
   l += __shfl_xor_sync(0xffffffffu, l, 8);
@@ -382,93 +367,196 @@ __global__ void __launch_bounds__(kThreads, 1) decode_attn_kernel(const DecodePa
     acch[i] += __shfl_xor_sync(0xffffffffu, acch[i], 16);
   }
 
-  if (p.n_splits == 1) {
-    // single split: this warp holds the whole row
-    if (row_ok) {
-      const float inv = l > 0.f ? 1.f / l : 0.f;
-      float habs = 0.f;
-      if (g == 0) {
-        HV ol, oh;
+  if constexpr (MODE == 1) {
+    // ---- cluster mode: partials never leave the chip ----------------------------------------------------
+    // Row `rl` of the cluster is finished by the cluster/rpc CTAs of rank slice*rpc + rl, each owning a DS-wide
+    // slice of D.  Every warp PUSHES its partial into the receive buffers of those CTAs (st.shared::cluster,
+    // fire and forget), one cluster barrier publishes them, and each CTA then merges from its own shared memory
+    // and exits -- no remote loads, no second barrier.
+    const int ds_sh = p.ds_shift;                       // DS = D * rpc / cluster is a power of two
+    const int DS = 1 << ds_sh;                          // dims per merging CTA
+    float* recv = reinterpret_cast<float*>(smem + kWarps * kWarpSmem + kWarps * kStages * 8);  // [n_splits][DS + 2]
+    {
+      const int rl = warp % p.rpc;
+      // after the xor-8/16 butterflies every key group holds the full sums: group g pushes 2 of the lane's 8+8 dims
 #pragma unroll
-        for (int i = 0; i < NH2; ++i) {
-          ol.h[i] = __floats2half2_rn(accl[2 * i] * inv, accl[2 * i + 1] * inv);
-          oh.h[i] = __floats2half2_rn(acch[2 * i] * inv, acch[2 * i + 1] * inv);
-          const float2 a = __half22float2(ol.h[i]), b = __half22float2(oh.h[i]);
-          habs += fabsf(a.x) + fabsf(a.y) + fabsf(b.x) + fabsf(b.y);
+      for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int e = 0; e < E2; ++e) {                                     // static register indices only
+          if (e / (E2 / 4) == g) {
+            const int dim = half * (D / 2) + c * E2 + e;
+            const float val = half ? acch[e] : accl[e];
+            const unsigned dst_cta = (dim >> ds_sh) * p.rpc + rl;
+            st_dsmem(recv + split * (DS + 2) + (dim & (DS - 1)), dst_cta, val);
+          }
         }
-        __half* o = p.out + static_cast<int64_t>(row) * D;
-        *reinterpret_cast<Vec*>(o + c * E2) = *reinterpret_cast<Vec*>(&ol);
-        *reinterpret_cast<Vec*>(o + D / 2 + c * E2) = *reinterpret_cast<Vec*>(&oh);
       }
-      if (p.head_importance) {
-        habs = warp_sum(habs);
-        if (lane == 0) atomicAdd(p.head_importance + h, habs);
+      if (lane < p.cluster / p.rpc) {                                      // (m, l) to every CTA that merges this row
+        const unsigned dst_cta = lane * p.rpc + rl;
+        st_dsmem(recv + split * (DS + 2) + DS, dst_cta, m);
+        st_dsmem(recv + split * (DS + 2) + DS + 1, dst_cta, l);
       }
-      if (p.importance && lg && live) {
-        __syncwarp();
-        float* imp = p.importance + static_cast<int64_t>(row) * p.imp_stride;
-        for (int j = lane; j < p.n_total; j += 32) {
-          __half s16 = lg[j];
-          if (mk) s16 = __hadd_rn(s16, mk[j]);
-          imp[j] += fast_exp2((__half2float(s16) - m) * kLog2e) * inv;
+    }
+    STAMP(4);
+    cluster_sync_all();
+    STAMP(5);
+    {
+      const int rl = range % p.rpc, slice = range / p.rpc;
+      const int mrow = rg * p.rpc + rl;
+      const int DW = DS / kWarps;                        // dims per warp: 2..16
+      if (mrow < p.rows) {
+        // lanes = splits: lane t owns split t (and t + 32)
+        float mj[2], lj[2], wj[2];
+        float M = -CUDART_INF_F;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int j = lane + 32 * t;
+          const bool ok = j < p.n_splits;
+          mj[t] = ok ? recv[j * (DS + 2) + DS] : -CUDART_INF_F;
+          lj[t] = ok ? recv[j * (DS + 2) + DS + 1] : 0.f;
+          M = fmaxf(M, mj[t]);
+        }
+        M = warp_max(M);
+        float L = 0.f;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          wj[t] = (M > -CUDART_INF_F) ? fast_exp2((mj[t] - M) * kLog2e) : 0.f;
+          L = fmaf(lj[t], wj[t], L);
+        }
+        L = warp_sum(L);
+        const float inv = L > 0.f ? 1.f / L : 0.f;
+        float habs = 0.f;
+#pragma unroll 1
+        for (int d0 = 0; d0 < DW; d0 += 4) {
+          float o[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int dl = warp * DW + d0 + i;                             // dim inside the slice
+            o[i] = 0.f;
+            if (d0 + i < DW) {
+              o[i] = wj[0] * recv[min(lane, p.n_splits - 1) * (DS + 2) + dl];
+              if (p.n_splits > 32) o[i] = fmaf(wj[1], recv[min(lane + 32, p.n_splits - 1) * (DS + 2) + dl], o[i]);
+            }
+          }
+#pragma unroll
+          for (int sft = 16; sft > 0; sft >>= 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] += __shfl_xor_sync(0xffffffffu, o[i], sft);
+          }
+          if (lane < 4 && d0 + lane < DW) {
+            const float mine = lane == 0 ? o[0] : (lane == 1 ? o[1] : (lane == 2 ? o[2] : o[3]));
+            const __half o16 = __float2half_rn(mine * inv);
+            p.out[static_cast<int64_t>(mrow) * D + slice * DS + warp * DW + d0 + lane] = o16;
+            habs += fabsf(__half2float(o16));
+          }
+        }
+        if (p.head_importance) {
+          habs = warp_sum(habs);
+          if (lane == 0) atomicAdd(p.head_importance + (mrow % p.H), habs);
+        }
+        if (slice == 0 && p.importance && p.logits && M > -CUDART_INF_F) {
+          const int mbq = mrow / p.H;
+          const __half* lgr = p.logits + (mbq / p.q_len) * p.logits_stride_b + (mrow % p.H) * p.logits_stride +
+                              (mbq % p.q_len) * p.logits_stride_q;
+          const __half* mkr = p.mask ? p.mask + static_cast<int64_t>(mbq) * p.n_total : nullptr;
+          float* imp = p.importance + static_cast<int64_t>(mrow) * p.imp_stride;
+#pragma unroll 1
+          for (int j = threadIdx.x; j < p.n_total; j += kThreads) {
+            __half s16 = __ushort_as_half(__ldcg(reinterpret_cast<const unsigned short*>(lgr) + j));
+            if (mkr) s16 = __hadd_rn(s16, mkr[j]);
+            imp[j] += fast_exp2((__half2float(s16) - M) * kLog2e) * inv;
+          }
         }
       }
     }
+    STAMP(6);
     return;
-  }
-
-  if (row_ok && g == 0) {
-    float* rec = p.part + (static_cast<int64_t>(row) * p.n_splits + split) * D;
+  } else {
+    if (p.n_splits == 1) {
+      // single split: this warp holds the whole row
+      if (row_ok) {
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+        float habs = 0.f;
+        if (g == 0) {
+          HV ol, oh;
 #pragma unroll
-    for (int i = 0; i < E2; i += 4) {
-      *reinterpret_cast<float4*>(rec + c * E2 + i) = make_float4(accl[i], accl[i + 1], accl[i + 2], accl[i + 3]);
-      *reinterpret_cast<float4*>(rec + D / 2 + c * E2 + i) = make_float4(acch[i], acch[i + 1], acch[i + 2], acch[i + 3]);
+          for (int i = 0; i < NH2; ++i) {
+            ol.h[i] = __floats2half2_rn(accl[2 * i] * inv, accl[2 * i + 1] * inv);
+            oh.h[i] = __floats2half2_rn(acch[2 * i] * inv, acch[2 * i + 1] * inv);
+            const float2 a = __half22float2(ol.h[i]), b = __half22float2(oh.h[i]);
+            habs += fabsf(a.x) + fabsf(a.y) + fabsf(b.x) + fabsf(b.y);
+          }
+          __half* o = p.out + static_cast<int64_t>(row) * D;
+          *reinterpret_cast<Vec*>(o + c * E2) = *reinterpret_cast<Vec*>(&ol);
+          *reinterpret_cast<Vec*>(o + D / 2 + c * E2) = *reinterpret_cast<Vec*>(&oh);
+        }
+        if (p.head_importance) {
+          habs = warp_sum(habs);
+          if (lane == 0) atomicAdd(p.head_importance + h, habs);
+        }
+        if (p.importance && lg && live) {
+          __syncwarp();
+          float* imp = p.importance + static_cast<int64_t>(row) * p.imp_stride;
+#pragma unroll 1
+          for (int j = lane; j < p.n_total; j += 32) {
+            __half s16 = lg[j];
+            if (mk) s16 = __hadd_rn(s16, mk[j]);
+            imp[j] += fast_exp2((__half2float(s16) - m) * kLog2e) * inv;
+          }
+        }
+      }
+      return;
     }
-    if (c == 0) p.part_ml[static_cast<int64_t>(row) * p.n_splits + split] = make_float2(m, l);
-  }
 
-  // ---- the last warp to finish a row merges that row's partials (per-row ticket) -----------------------
-  STAMP(4);   // partial written
-  __syncwarp();
-  unsigned prev = 0;
-  if (lane == 0 && row_ok) {
-    __threadfence();                                   // release: the warp's partial is visible device-wide
-    prev = atomicAdd(p.counters + row, 1u);
-  }
-  prev = __shfl_sync(0xffffffffu, prev, 0);
-  STAMP(5);   // ticket taken
-  if (!row_ok || prev != static_cast<unsigned>(p.n_splits - 1)) return;
-  __threadfence();                                     // acquire side
+    if (row_ok && g == 0) {
+      float* rec = p.part + (static_cast<int64_t>(row) * p.n_splits + split) * D;
+#pragma unroll
+      for (int i = 0; i < E2; i += 4) {
+        *reinterpret_cast<float4*>(rec + c * E2 + i) = make_float4(accl[i], accl[i + 1], accl[i + 2], accl[i + 3]);
+        *reinterpret_cast<float4*>(rec + D / 2 + c * E2 + i) = make_float4(acch[i], acch[i + 1], acch[i + 2], acch[i + 3]);
+      }
+      if (c == 0) p.part_ml[static_cast<int64_t>(row) * p.n_splits + split] = make_float2(m, l);
+    }
 
-  // the K/V ring is dead now: reuse the warp's slice for the split weights
-  float* wts = reinterpret_cast<float*>(wsm);
-  static_assert(kWarpSmem >= kMaxSplits * 4, "ring slice too small for the merge weights");
-  {
+    // ---- the last warp to finish a row merges that row's partials (per-row ticket) -----------------------
+    STAMP(4);   // partial written
+    __syncwarp();
+    unsigned prev = 0;
+    if (lane == 0 && row_ok) {
+      __threadfence();                                   // release: the warp's partial is visible device-wide
+      prev = atomicAdd(p.counters + row, 1u);
+    }
+    prev = __shfl_sync(0xffffffffu, prev, 0);
+    STAMP(5);   // ticket taken
+    if (!row_ok || prev != static_cast<unsigned>(p.n_splits - 1)) return;
+    __threadfence();                                     // acquire side
+
+    // the K/V ring is dead now: reuse the warp's slice for the split weights
+    float* wts = reinterpret_cast<float*>(wsm);
+    static_assert(kWarpSmem >= kMaxSplits * 4, "ring slice too small for the merge weights");
     const float* rec = p.part + static_cast<int64_t>(row) * p.n_splits * D;
     const float2* ml = p.part_ml + static_cast<int64_t>(row) * p.n_splits;
-    // weights of the splits: all (m, l) loads are independent and issued together
-    constexpr int kPerLane = kMaxSplits / 32;
-    float2 mls[kPerLane];
+    constexpr int PER = D / 32;   // output dims per lane: 4 (D=128) or 2 (D=64)
+    using PV_t = typename VecT<PER * 4>::type;
+    constexpr int kU = 40;        // partial loads in flight per lane: one batch covers the usual <= 40 splits
+    PV_t v[kU];
+    // everything the merge needs is requested at once: the (m, l) pairs and the first batch of partials
+    float2 mls[kMaxSplits / 32];
 #pragma unroll
-    for (int k = 0; k < kPerLane; ++k) {
+    for (int k = 0; k < kMaxSplits / 32; ++k) {
       const int sidx = lane + 32 * k;
       mls[k] = sidx < p.n_splits ? __ldcg(ml + sidx) : make_float2(-CUDART_INF_F, 0.f);
     }
-    constexpr int PER = D / 32;   // output dims per lane: 4 (D=128) or 2 (D=64)
-    using PV_t = typename VecT<PER * 4>::type;
-    constexpr int kU = 20;        // independent partial loads in flight per lane
-    PV_t v[kU];
 #pragma unroll
-    for (int u = 0; u < kU; ++u)   // first batch of partials: issued before the weights are known
+    for (int u = 0; u < kU; ++u)
       v[u] = __ldcg(reinterpret_cast<const PV_t*>(rec + static_cast<int64_t>(min(u, p.n_splits - 1)) * D + lane * PER));
     float M = -CUDART_INF_F;
 #pragma unroll
-    for (int k = 0; k < kPerLane; ++k) M = fmaxf(M, mls[k].x);
+    for (int k = 0; k < kMaxSplits / 32; ++k) M = fmaxf(M, mls[k].x);
     M = warp_max(M);
-    STAMP(7);   // (m, l) of every split arrived
     float L = 0.f;
 #pragma unroll
-    for (int k = 0; k < kPerLane; ++k) {
+    for (int k = 0; k < kMaxSplits / 32; ++k) {
       const int sidx = lane + 32 * k;
       const float w = (M > -CUDART_INF_F) ? fast_exp2((mls[k].x - M) * kLog2e) : 0.f;
       if (sidx < p.n_splits) wts[sidx] = w;
@@ -476,9 +564,11 @@ __global__ void __launch_bounds__(kThreads, 1) decode_attn_kernel(const DecodePa
     }
     L = warp_sum(L);
     __syncwarp();
+    STAMP(7);   // (m, l) of every split arrived
     float o[PER];
 #pragma unroll
     for (int i = 0; i < PER; ++i) o[i] = 0.f;
+#pragma unroll 1
     for (int s0 = 0; s0 < p.n_splits; s0 += kU) {
       if (s0 > 0) {
 #pragma unroll
@@ -510,15 +600,17 @@ __global__ void __launch_bounds__(kThreads, 1) decode_attn_kernel(const DecodePa
     }
     if (p.importance && p.logits && M > -CUDART_INF_F) {
       float* imp = p.importance + static_cast<int64_t>(row) * p.imp_stride;
+#pragma unroll 1
       for (int j = lane; j < p.n_total; j += 32) {
         __half s16 = __ushort_as_half(__ldcg(reinterpret_cast<const unsigned short*>(lg) + j));
         if (mk) s16 = __hadd_rn(s16, mk[j]);
         imp[j] += fast_exp2((__half2float(s16) - M) * kLog2e) * inv;
       }
     }
+    STAMP(6);   // merged
+    if (lane == 0) p.counters[row] = 0;         // self-cleaning ticket for the next launch
   }
-  STAMP(6);   // merged
-  if (lane == 0) p.counters[row] = 0;         // self-cleaning ticket for the next launch
+#undef STAMP
 }
 
 // ---- host side ------------------------------------------------------------------------------------------
@@ -544,35 +636,91 @@ static void choose_split(int rows, int n_total, int sms, int& rpc, int& spc, int
   }
 }
 
+// K/V rings + mbarriers + (cluster mode) the receive buffer for pushed partials: n_splits * (DS + 2) floats with
+// n_splits * DS == 8 * D and n_splits <= 64
 template <int D>
-static int launch_decode(const DecodeParams& p, cudaStream_t st) {
-  constexpr size_t smem = static_cast<size_t>(kWarps) * kStages * 2 * kTile * D * 2 + kWarps * kStages * 8;
-  static bool configured[64] = {};
+constexpr size_t decode_smem_bytes() {
+  return static_cast<size_t>(kWarps) * kStages * 2 * kTile * D * 2 + kWarps * kStages * 8 +
+         (static_cast<size_t>(kWarps) * D + 2 * 64) * sizeof(float);
+}
+
+using DecodeKernel = void (*)(const DecodeParams);
+
+template <int D>
+static DecodeKernel decode_kernel(int mode, bool dbg) {
+  if (D == 128 && dbg) return mode ? decode_attn_kernel<128, 1, true> : decode_attn_kernel<128, 0, true>;
+  return mode ? decode_attn_kernel<D, 1, false> : decode_attn_kernel<D, 0, false>;
+}
+
+template <int D>
+static int configure_decode(DecodeKernel k, int slot) {
+  static bool configured[64][4] = {};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 64 && !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(decode_attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
+  if (dev < 64 && !configured[dev][slot]) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(decode_smem_bytes<D>()));
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(decode_attn_kernel)");
-    configured[dev] = true;
+    configured[dev][slot] = true;
   }
-  cudaError_t e;
+  return SPATTEN_OK;
+}
+
+// How many clusters of `cs` CTAs of the cluster-mode kernel the device can hold at once (GPC-granular).
+template <int D>
+static int max_active_clusters(int cs) {
+  static int cached[64][kMaxClusterSize + 1] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && cached[dev][cs] != 0) return cached[dev][cs];
+  DecodeKernel k = decode_kernel<D>(1, false);
+  if (configure_decode<D>(k, 1) != SPATTEN_OK) return 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(cs * 64);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = decode_smem_bytes<D>();
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, k, &cfg) != cudaSuccess) { cudaGetLastError(); n = -1; }
+  if (dev < 64) cached[dev][cs] = n > 0 ? n : -1;
+  return n;
+}
+
+template <int D>
+static int launch_decode(const DecodeParams& p, cudaStream_t st) {
+  constexpr size_t smem = decode_smem_bytes<D>();
+  const bool dbg = p.dbg != nullptr && D == 128;
+  const int mode = p.cluster ? 1 : 0;
+  DecodeKernel k = decode_kernel<D>(mode, dbg);
+  if (int rc = configure_decode<D>(k, mode + (dbg ? 2 : 0))) return rc;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p.cluster ? p.n_rg * p.cluster : p.n_rg * p.n_ranges);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
   if (p.pdl) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(p.n_rg * p.n_ranges);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, decode_attn_kernel<D>, p);
-  } else {
-    decode_attn_kernel<D><<<p.n_rg * p.n_ranges, kThreads, smem, st>>>(p);
-    e = cudaGetLastError();
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
   }
+  if (p.cluster) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = p.cluster;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k, p);
   if (e != cudaSuccess) return cuda_fail(e, "decode_attn_kernel launch");
   return SPATTEN_OK;
 }
@@ -583,6 +731,11 @@ using namespace spatten;
 
 static unsigned long long* g_dbg = nullptr;
 // Debug hook (not part of the public header): device buffer of [grid][8][8] u64 receiving %globaltimer stamps.
+// Debug hook: how many 8-CTA clusters of the decode kernel the current device holds at once.
+extern "C" int spatten_debug_max_clusters(int head_dim) {
+  return (head_dim == 128 ? max_active_clusters<128>(8) : max_active_clusters<64>(8)) * 1000 +
+         (head_dim == 128 ? max_active_clusters<128>(4) : max_active_clusters<64>(4));
+}
 extern "C" void spatten_debug_set_timeline(unsigned long long* dev_buf) { g_dbg = dev_buf; }
 
 extern "C" size_t spatten_decode_workspace_bytes(int32_t batch, int32_t num_heads, int32_t head_dim) {
@@ -663,6 +816,7 @@ extern "C" int spatten_decode_attn(const SpattenDecodeArgs* a, void* stream) {
   p.rows = a->batch * q_len * a->num_heads;
   p.sqrt_d = static_cast<float>(sqrt(static_cast<double>(a->head_dim)));
   p.rsqrt_d = 1.0f / p.sqrt_d;
+
   p.pdl = 0;
   if (a->flags & SPATTEN_DECODE_PDL) p.pdl = 1;
   if ((a->flags & SPATTEN_DECODE_PDL_KV_STABLE) && (a->flags & SPATTEN_DECODE_PDL) && a->head_mask == nullptr) p.pdl = 2;
@@ -672,8 +826,32 @@ extern "C" int spatten_decode_attn(const SpattenDecodeArgs* a, void* stream) {
   if (sms <= 0) return SPATTEN_ERR_CUDA;
   choose_split(p.rows, n_total, sms, p.rpc, p.spc, p.n_rg, p.n_ranges);
   p.n_splits = p.n_ranges * p.spc;
-  p.tok_per_split = (n_total + p.n_splits - 1) / p.n_splits;
-  if (p.n_splits > 1) {
+  p.cluster = 0;
+  // Cluster mode: all splits of a row inside one thread-block cluster (8 or 4 CTAs), merged over DSMEM -- no
+  // global partials, no tickets.  Taken when some (cluster size, rows per CTA) fills >= 3/4 of the SMs in ONE
+  // wave of clusters and every warp still gets >= 16 cached tokens; the candidate with the most CTAs wins, ties
+  // go to more rows per CTA (more RoPE-row sharing).  Big-row-count shapes stay in ticket mode.
+  if (!(a->flags & SPATTEN_DECODE_NO_CLUSTER)) {
+    int best_ctas = 0;
+    for (int cs = kMaxClusterSize; cs >= 4; cs >>= 1) {
+      const int max_cl = a->head_dim == 128 ? max_active_clusters<128>(cs) : max_active_clusters<64>(cs);
+      for (int rpc = 8; rpc >= 1 && max_cl > 0; rpc >>= 1) {
+        const int n_cl = (p.rows + rpc - 1) / rpc;
+        const int spc = kWarps / rpc;
+        const int ctas = n_cl * cs;
+        if (n_cl > max_cl || ctas > sms || ctas * 4 < sms * 3 || ctas <= best_ctas) continue;
+        if (a->kv_len < cs * spc * 16) continue;
+        best_ctas = ctas;
+        p.cluster = cs;
+        p.rpc = rpc; p.spc = spc; p.n_rg = n_cl; p.n_ranges = cs;
+        p.n_splits = cs * spc;
+        p.ds_shift = 0;
+        while ((1 << p.ds_shift) < a->head_dim * rpc / cs) ++p.ds_shift;
+      }
+    }
+  }
+  p.tok_per_split = (std::max(a->kv_len, 1) + p.n_splits - 1) / p.n_splits;
+  if (p.n_splits > 1 && !p.cluster) {
     const size_t need = spatten_decode_workspace_bytes(a->batch, a->num_heads, a->head_dim);
     if (a->workspace == nullptr || a->workspace_bytes < need) {
       set_error("spatten_decode_attn: workspace %zu bytes < required %zu", a->workspace_bytes, need);

@@ -15,7 +15,7 @@ DECODE_CASES = [c for c in FWD_CASES if c.q_len == 1 and c.dtype == "fp16"]
 
 
 def run_kernel(q, k_new, v_new, past_k, past_v, position_ids, mask, cap_pad=5, want_importance=False,
-               head_mask=None):
+               head_mask=None, flags=0):
     from spatten_b200 import ops
     dev = "cuda"
     b, H, _, D = q.shape
@@ -35,7 +35,7 @@ def run_kernel(q, k_new, v_new, past_k, past_v, position_ids, mask, cap_pad=5, w
     out = ops.decode_attn(q[:, :, 0].contiguous().to(dev), kc, vc, past, rope,
                           k_new=k_new[:, :, 0].contiguous().to(dev), v_new=v_new[:, :, 0].contiguous().to(dev),
                           q_pos=position_ids[:, 0].contiguous().to(dev), mask=m, logits=logits,
-                          importance=imp, head_importance=himp,
+                          importance=imp, head_importance=himp, flags=flags,
                           head_mask=None if head_mask is None else head_mask.to(dev))
     torch.cuda.synchronize()
     return out.cpu(), logits[:, :, :past + 1].cpu(), kc.cpu(), vc.cpu(), imp, himp
@@ -98,6 +98,32 @@ def test_decode_matches_oracle(b, H, H_kv, D, past):
     assert torch.allclose(imp.cpu(), p, rtol=2e-3, atol=1e-6)
     hi = out.float().abs().sum(dim=(0, 2))
     assert torch.allclose(himp.cpu(), hi, rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("b,H,D,past", [(1, 32, 128, 2047), (2, 16, 128, 2047), (8, 4, 128, 1500), (1, 64, 64, 777),
+                                        (1, 128, 128, 600), (1, 30, 128, 2047)])
+def test_cluster_and_ticket_variants_agree(b, H, D, past):
+    """The DSMEM-merge (thread-block cluster) variant and the global-ticket variant are the same function."""
+    from spatten_b200 import _lib
+    seed = 7000 + H + past
+    q = det_normal((b, H, 1, D), seed, 1.0, torch.float16)
+    k = det_normal((b, H, 1, D), seed + 1, 1.0, torch.float16)
+    v = det_normal((b, H, 1, D), seed + 2, 1.0, torch.float16)
+    pk = det_normal((b, H, past, D), seed + 3, 1.0, torch.float16)
+    pv = det_normal((b, H, past, D), seed + 4, 1.0, torch.float16)
+    pos = torch.full((b, 1), past, dtype=torch.int64)
+    ref_out, ref_scores, _ = O.attn_forward_core(q, k, v, pk, pv, pos, None)
+    res = {}
+    for name, fl in (("cluster", 0), ("ticket", _lib.DECODE_NO_CLUSTER)):
+        out, logits, kc, vc, imp, himp = run_kernel(q, k, v, pk, pv, pos, None, want_importance=True, flags=fl)
+        assert_logits_close(logits, ref_scores[:, :, 0, :], name)
+        assert rel_err(out, ref_out[:, :, 0, :]) <= OUT_REL_TOL, name
+        assert torch.equal(kc[:, :, past], k[:, :, 0]) and torch.equal(vc[:, :, past], v[:, :, 0])
+        res[name] = (out, logits, imp.cpu(), himp.cpu())
+    assert torch.equal(res["cluster"][1], res["ticket"][1])                     # logits: bit-identical
+    assert rel_err(res["cluster"][0], res["ticket"][0]) <= 1e-3
+    assert torch.allclose(res["cluster"][2], res["ticket"][2], rtol=1e-3, atol=1e-7)
+    assert torch.allclose(res["cluster"][3], res["ticket"][3], rtol=1e-3, atol=1e-3)
 
 
 def test_decode_head_mask_and_noappend():

@@ -56,7 +56,7 @@ def bench_shape(b, H, D, n, L, iters, logits_on=True, graph=True, flags=0):
             "frac_6445": round(bytes_layer / us_layer / 1e3 / 6445, 4)}
 
 
-def timeline(b, H, D, n, L):
+def timeline(b, H, D, n, L, flags=0):
     """Phase timeline of the LAST of L back-to-back launches (warm caches), from %globaltimer stamps."""
     import ctypes as C
     import numpy as np
@@ -74,7 +74,7 @@ def timeline(b, H, D, n, L):
         for l in range(L):
             if rep == 2 and l == L - 1:
                 lib.spatten_debug_set_timeline(C.c_void_p(buf.data_ptr()))
-            ops.decode_attn(q[l], kc[l], vc[l], n - 1, rope, k_new=q[l], v_new=q[l], logits=logits[l])
+            ops.decode_attn(q[l], kc[l], vc[l], n - 1, rope, k_new=q[l], v_new=q[l], logits=logits[l], flags=flags)
     torch.cuda.synchronize()
     lib.spatten_debug_set_timeline(None)
     t = buf.cpu().numpy().reshape(-1, 8, 8).astype(np.float64)
@@ -86,10 +86,13 @@ def timeline(b, H, D, n, L):
     for k, nm in enumerate(names):
         v = t[:, :, k]
         v = v[v > 0] - t0
-        if k >= 6:   # merge-only stamps: report relative to the same warp's ticket stamp
-            sel = t[:, :, k] > 0
+        if k >= 6:   # merge-only stamps: report relative to the same warp's ticket stamp (merging warps only)
+            sel = (t[:, :, k] > 0) & (t[:, :, 5] > 0)
+            if k == 6 and (t[:, :, 7] > 0).sum() == 0:
+                sel &= np.arange(8)[None, :] == 0          # cluster mode: warp 0 of every CTA merges
             dv = (t[:, :, k] - t[:, :, 5])[sel]
-            print(f"  {nm:16s} after own ticket: min {dv.min():6.0f} median {np.median(dv):6.0f} max {dv.max():6.0f}")
+            if dv.size:
+                print(f"  {nm:16s} after own ticket: min {dv.min():6.0f} median {np.median(dv):6.0f} max {dv.max():6.0f}")
         if v.size:
             print(f"  {nm:16s} min {v.min():8.0f}  median {np.median(v):8.0f}  max {v.max():8.0f}  (n={v.size})")
 
@@ -100,9 +103,10 @@ if __name__ == "__main__":
     ap.add_argument("--shape", type=str, default=None, help="b,H,D,n,L: run only this shape (for ncu)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--timeline", action="store_true", help="dump per-phase globaltimer stamps for one launch")
+    ap.add_argument("--flags", type=int, default=0)
     a = ap.parse_args()
     if a.timeline:
-        timeline(*map(int, (a.shape or "1,32,128,2048,32").split(",")))
+        timeline(*map(int, (a.shape or "1,32,128,2048,32").split(",")), flags=a.flags)
         sys.exit(0)
     if a.shape:
         b, H, D, n, L = map(int, a.shape.split(","))
@@ -111,6 +115,6 @@ if __name__ == "__main__":
     shapes = [(1, 32, 128, 2048, 32), (1, 32, 128, 4096, 32), (1, 32, 128, 8192, 16), (8, 5, 128, 16384, 8),
               (1, 4, 128, 2048, 32), (1, 32, 128, 512, 32)]
     for (b, H, D, n, L) in shapes:
-        for fl in (0, 1, 3):
+        for fl in (0, 3, 4, 7):
             print(json.dumps(bench_shape(b, H, D, n, L, a.iters, True, flags=fl)), flush=True)
     print(json.dumps(bench_shape(1, 32, 128, 2048, 32, a.iters, True, graph=False)), flush=True)
