@@ -234,19 +234,15 @@ def run_ours(args):
     def attn_layer(l):
         _lib.check(lib.spatten_decode_attn(C.byref(layer_args[l]), sptr))
 
+    from spatten_b200.parallel import HeadShard, exchange_heads
+    shard = HeadShard(rank, world, H)
+
     def collective(l):
-        if world > 1:
-            if args.collective == "allgather":
-                dist.all_gather_into_tensor(gathered[l], gathered[l, rank])
-            else:
-                dist.all_reduce(gathered[l])
+        # zero-padded all-reduce (re-zeroes the peers' slots first) or all-gather of the per-rank head blocks
+        exchange_heads(gathered[l], shard, args.collective)
 
     def rezero(l):
-        # the literal all-reduce needs the peers' slots zero before every reduction
-        if world > 1 and args.collective == "allreduce":
-            for r in range(world):
-                if r != rank:
-                    gathered[l, r].zero_()
+        pass
 
     def step_eager(with_collective=True):
         for l in range(L):

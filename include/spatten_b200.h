@@ -62,6 +62,10 @@ int spatten_device_info(int* sm_count, int* cc_major, int* cc_minor);
 #define SPATTEN_DECODE_PDL_KV_STABLE 2u
 /* Never use the thread-block-cluster (DSMEM merge) variant; always global partials + tickets. */
 #define SPATTEN_DECODE_NO_CLUSTER 4u
+/* DotProduct stage only: stream K, export the logits, skip softmax / P.V / out (V is not read; v_new is still
+ * appended).  First step of the RTL-ordered path DotProduct -> TopK -> MultiplyValue over survivors
+ * (SpAttenController.scala:347,588,668-749); see spatten_sparse_pv. */
+#define SPATTEN_DECODE_SCORES_ONLY 8u
 
 typedef struct SpattenDecodeArgs {
   uint32_t struct_size;   /* = sizeof(SpattenDecodeArgs), ABI guard */
@@ -179,6 +183,37 @@ typedef struct SpattenGatherArgs {
   int64_t keep_stride;
 } SpattenGatherArgs;
 int spatten_kv_gather(const SpattenGatherArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * RTL-named stages that the reference Python never executes (README.md:11,21; "parity unpinned":
+ * checked against the self-consistent restatements in oracle/spatten_oracle.py).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* "Local V pruning": MultiplyValue over the top-k survivors only (SpAttenController.scala:554,588-591,
+ * 668-726,749).  For every (b,h) row: p = softmax(logits[row, keep_idx[row, :]]) in fp32,
+ * out[row, :] = sum_i p_i * V[row, keep_idx[row, i], :].  Only the kept V rows are read from HBM.
+ * logits: fp16 [rows, logits_stride] (spatten_decode_attn with SPATTEN_DECODE_SCORES_ONLY),
+ * keep_idx: int32 [rows, keep_stride] ascending (spatten_topk_select with start = recent = 0),
+ * v_cache: fp16 [batch, num_kv_heads, >= max index + 1, head_dim]; rows = batch * num_heads. */
+typedef struct SpattenSparsePvArgs {
+  uint32_t struct_size;
+  int32_t batch, num_heads, num_kv_heads, head_dim, keep;
+  const void* logits;
+  int64_t logits_stride;
+  const int32_t* keep_idx;
+  int64_t keep_stride;
+  const void* v_cache;
+  int64_t cache_stride_b, cache_stride_h;   /* elements */
+  void* out;                                 /* fp16 [batch, num_heads, head_dim] */
+} SpattenSparsePvArgs;
+int spatten_sparse_pv(const SpattenSparsePvArgs* args, void* stream);
+
+/* Head pruning (README.md:21 "head pruning to remove unessential heads"): mask[h] = 1 for the `keep_heads`
+ * heads with the largest cumulative importance (fp32 [num_heads], accumulated by spatten_decode_attn's
+ * `head_importance` output), ties -> lowest head index; 0 elsewhere.  The mask is what spatten_decode_attn
+ * takes as `head_mask`: pruned heads read no KV at all. */
+int spatten_head_select(const float* head_importance, int32_t num_heads, int32_t keep_heads, uint8_t* head_mask,
+                        void* stream);
 
 #ifdef __cplusplus
 }

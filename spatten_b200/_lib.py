@@ -16,6 +16,7 @@ SPATTEN_OK = 0
 DECODE_PDL = 1
 DECODE_PDL_KV_STABLE = 2
 DECODE_NO_CLUSTER = 4
+DECODE_SCORES_ONLY = 8
 ERR_NAMES = {-1: "SPATTEN_ERR_INVALID", -2: "SPATTEN_ERR_UNSUPPORTED", -3: "SPATTEN_ERR_CUDA",
              -4: "SPATTEN_ERR_WORKSPACE"}
 
@@ -65,6 +66,18 @@ class GatherArgs(C.Structure):
     ]
 
 
+class SparsePvArgs(C.Structure):
+    """Mirror of `SpattenSparsePvArgs`."""
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("batch", C.c_int32), ("num_heads", C.c_int32), ("num_kv_heads", C.c_int32),
+        ("head_dim", C.c_int32), ("keep", C.c_int32),
+        ("logits", C.c_void_p), ("logits_stride", C.c_int64),
+        ("keep_idx", C.c_void_p), ("keep_stride", C.c_int64),
+        ("v_cache", C.c_void_p), ("cache_stride_b", C.c_int64), ("cache_stride_h", C.c_int64),
+        ("out", C.c_void_p),
+    ]
+
+
 DTYPE_F16, DTYPE_F32 = 0, 1
 
 _lib = None
@@ -102,6 +115,8 @@ def _bind_optional(lib):
                                          C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
     lib.spatten_topk_select.argtypes = [C.POINTER(SelectArgs), C.c_void_p]
     lib.spatten_kv_gather.argtypes = [C.POINTER(GatherArgs), C.c_void_p]
+    lib.spatten_sparse_pv.argtypes = [C.POINTER(SparsePvArgs), C.c_void_p]
+    lib.spatten_head_select.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
 
 
 def check(code: int):

@@ -66,6 +66,7 @@ struct DecodeParams {
   int rows, rpc, spc, n_rg, n_ranges, n_splits, tok_per_split;
   float sqrt_d, rsqrt_d;
   int pdl;                 // launched with programmatic stream serialization (SPATTEN_DECODE_PDL)
+  int scores_only;         // SPATTEN_DECODE_SCORES_ONLY: stream K only, export logits, no softmax / P.V / out
   int ds_shift;            // cluster mode: log2(D * rpc / cluster)
   int cluster;             // 0: global partials + per-row tickets; 4 or 8: every split of a row lives in one
                            // thread-block cluster of that size and partials are merged through distributed shared memory
@@ -191,9 +192,10 @@ __global__ void __launch_bounds__(kThreads, 1) decode_attn_kernel(const DecodePa
     const int ncopy = min(kTile, t1c - tok);            // rows that come from the cache (the new token does not)
     if (ncopy <= 0) return;
     const uint32_t bytes = static_cast<uint32_t>(ncopy) * kRowBytes;
-    mbar_expect_tx(&bars[s], 2 * bytes);
+    mbar_expect_tx(&bars[s], p.scores_only ? bytes : 2 * bytes);
     bulk_g2s(wsm + s * 2 * kTileBytes, Kc + static_cast<int64_t>(tok) * D, bytes, &bars[s], pol);
-    bulk_g2s(wsm + s * 2 * kTileBytes + kTileBytes, Vc + static_cast<int64_t>(tok) * D, bytes, &bars[s], pol);
+    if (!p.scores_only)
+      bulk_g2s(wsm + s * 2 * kTileBytes + kTileBytes, Vc + static_cast<int64_t>(tok) * D, bytes, &bars[s], pol);
   };
   if (lane == 0) {
 #pragma unroll
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_attn_kernel(const DecodePa
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
     const float m_new = fmaxf(m, mx);
-    if (m_new > -CUDART_INF_F) {
+    if (m_new > -CUDART_INF_F && !p.scores_only) {
       if (m_new != m) {                         // warp-uniform: rescale only when the running max moved
         const float corr = fast_exp2((m - m_new) * kLog2e);
         l *= corr;
@@ -355,6 +357,10 @@ __global__ void __launch_bounds__(kThreads, 1) decode_attn_kernel(const DecodePa
     for (int ps = 0; ps < kPasses; ++ps) { cs[ps] = csn[ps]; sn[ps] = snn[ps]; }
   }
   STAMP(3);   // streaming loop done
+  if (p.scores_only) {
+    if constexpr (MODE == 1) cluster_sync_all();   // cluster CTAs leave together
+    return;
+  }
 
   // ---- merge the 4 key groups of the warp -------------------------------------------------------------
   l += __shfl_xor_sync(0xffffffffu, l, 8);
@@ -768,7 +774,8 @@ extern "C" int spatten_decode_attn(const SpattenDecodeArgs* a, void* stream) {
   SPATTEN_CHECK_ARG(static_cast<int64_t>(a->batch) * q_len * a->num_heads < (1ll << 31), "spatten_decode_attn: too many rows");
   SPATTEN_CHECK_ARG(n_total > 0, "spatten_decode_attn: nothing to attend over (kv_len 0 and append 0)");
   SPATTEN_CHECK_ARG(a->rope_len >= n_total, "spatten_decode_attn: rope_len %d < kv_len+append %d", a->rope_len, n_total);
-  SPATTEN_CHECK_ARG(a->q && a->k_cache && a->v_cache && a->rope && a->out, "spatten_decode_attn: NULL q/k_cache/v_cache/rope/out");
+  SPATTEN_CHECK_ARG(a->q && a->k_cache && a->v_cache && a->rope, "spatten_decode_attn: NULL q/k_cache/v_cache/rope");
+  SPATTEN_CHECK_ARG(a->out || (a->flags & SPATTEN_DECODE_SCORES_ONLY), "spatten_decode_attn: NULL out");
   SPATTEN_CHECK_ARG(!a->append || (a->k_new && a->v_new), "spatten_decode_attn: append=1 needs k_new and v_new");
   SPATTEN_CHECK_ARG(a->cache_stride_h >= static_cast<int64_t>(n_total) * a->head_dim,
                     "spatten_decode_attn: cache_stride_h %lld too small for %d tokens", (long long)a->cache_stride_h, n_total);
@@ -817,6 +824,8 @@ extern "C" int spatten_decode_attn(const SpattenDecodeArgs* a, void* stream) {
   p.sqrt_d = static_cast<float>(sqrt(static_cast<double>(a->head_dim)));
   p.rsqrt_d = 1.0f / p.sqrt_d;
 
+  p.scores_only = (a->flags & SPATTEN_DECODE_SCORES_ONLY) ? 1 : 0;
+  SPATTEN_CHECK_ARG(!p.scores_only || a->logits != nullptr, "spatten_decode_attn: SCORES_ONLY needs a logits buffer");
   p.pdl = 0;
   if (a->flags & SPATTEN_DECODE_PDL) p.pdl = 1;
   if ((a->flags & SPATTEN_DECODE_PDL_KV_STABLE) && (a->flags & SPATTEN_DECODE_PDL) && a->head_mask == nullptr) p.pdl = 2;

@@ -77,7 +77,7 @@ def make_decode_args(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tens
     if append:
         k_new, v_new = k_new.contiguous(), v_new.contiguous()
     if out is None:
-        out = torch.empty(q.shape, dtype=torch.float16, device=q.device)
+        out = None if (flags & _lib.DECODE_SCORES_ONLY) else torch.empty(q.shape, dtype=torch.float16, device=q.device)
     elif not out.is_contiguous() or out.numel() != q.numel():
         raise ValueError("out must be contiguous with q's shape")
     a = _lib.DecodeArgs()
@@ -100,7 +100,7 @@ def make_decode_args(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tens
         a.mask = mask.data_ptr()
     if head_mask is not None:
         a.head_mask = head_mask.data_ptr()
-    a.out = out.data_ptr()
+    a.out = out.data_ptr() if out is not None else None
     if logits is not None:
         if logits.dtype != torch.float16 or logits.stride(-1) != 1:
             raise ValueError("logits must be fp16 with a contiguous last dimension")
@@ -244,3 +244,68 @@ def kv_gather(k: torch.Tensor, v: torch.Tensor, keep_idx: torch.Tensor, k_out: O
     with torch.cuda.device(k.device):
         _lib.check(lib.spatten_kv_gather(C.byref(a), C.c_void_p(_stream_ptr(k.device))))
     return k_out, v_out
+
+
+# ------------------------------------------------------------------------------------------------------
+# RTL-ordered stages (parity unpinned): local V pruning and head pruning
+# ------------------------------------------------------------------------------------------------------
+
+def sparse_pv(logits: torch.Tensor, keep_idx: torch.Tensor, v_cache: torch.Tensor, num_heads: int) -> torch.Tensor:
+    """out[b,h,:] = softmax(logits[b,h,keep]) @ V[b,h,keep,:]  -- `spatten_sparse_pv`.
+
+    logits fp16 [b*H, >=n] (or [b,H,>=n]); keep_idx int32 [b*H, keep] ascending; v_cache fp16 [b,H_kv,cap,D].
+    """
+    lib = _lib.load()
+    _require_cuda(logits, keep_idx, v_cache)
+    b, H_kv, _, D = v_cache.shape
+    lg = logits.reshape(b * num_heads, logits.shape[-1]) if logits.dim() == 3 else logits
+    if lg.stride(-1) != 1 or keep_idx.dtype != torch.int32 or keep_idx.shape[0] != b * num_heads:
+        raise ValueError("sparse_pv: logits rows must be contiguous; keep_idx must be int32 [b*H, keep]")
+    out = torch.empty((b, num_heads, D), dtype=torch.float16, device=v_cache.device)
+    a = _lib.SparsePvArgs()
+    a.struct_size = C.sizeof(_lib.SparsePvArgs)
+    a.batch, a.num_heads, a.num_kv_heads, a.head_dim, a.keep = b, num_heads, H_kv, D, keep_idx.shape[1]
+    a.logits, a.logits_stride = lg.data_ptr(), lg.stride(0)
+    a.keep_idx, a.keep_stride = keep_idx.data_ptr(), keep_idx.stride(0)
+    a.v_cache, a.cache_stride_b, a.cache_stride_h = v_cache.data_ptr(), v_cache.stride(0), v_cache.stride(1)
+    a.out = out.data_ptr()
+    with torch.cuda.device(v_cache.device):
+        _lib.check(lib.spatten_sparse_pv(C.byref(a), C.c_void_p(_stream_ptr(v_cache.device))))
+    return out
+
+
+def local_v_attn(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, kv_len: int, rope: torch.Tensor,
+                 keep_v: int, k_new: Optional[torch.Tensor] = None, v_new: Optional[torch.Tensor] = None,
+                 q_pos: Optional[torch.Tensor] = None):
+    """RTL stage order (SpAttenController.scala:347-749): DotProduct over ALL cached keys -> TopK(keep_v) ->
+    MultiplyValue over the survivors only.  Three launches, no host sync.  Returns (out [b,H,D], logits
+    [b,H,n], keep_idx int32 [b*H, keep_v] ascending).  HBM traffic: N keys + keep_v values per head.
+    """
+    b, H, D = q.shape
+    n = int(kv_len) + (1 if k_new is not None else 0)
+    logits = torch.empty((b, H, n), dtype=torch.float16, device=q.device)
+    a, _, _keep = make_decode_args(q, k_cache, v_cache, kv_len, rope, k_new=k_new, v_new=v_new, q_pos=q_pos,
+                                   logits=logits, flags=_lib.DECODE_SCORES_ONLY)
+    with torch.cuda.device(q.device):
+        _lib.check(_lib.load().spatten_decode_attn(C.byref(a), C.c_void_p(_stream_ptr(q.device))))
+    rows = logits.view(b * H, n)
+    if keep_v >= n:
+        keep = torch.arange(n, dtype=torch.int32, device=q.device).expand(b * H, n).contiguous()
+    else:
+        keep = topk_select(rows, n, 0, 0, keep_v, 0)
+    return sparse_pv(rows, keep, v_cache, H), logits, keep
+
+
+def head_select(head_importance: torch.Tensor, keep_heads: int, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """u8 [H] mask of the `keep_heads` most important heads (ties -> lowest index) -- `spatten_head_select`."""
+    lib = _lib.load()
+    _require_cuda(head_importance, mask)
+    if head_importance.dtype != torch.float32 or not head_importance.is_contiguous():
+        raise TypeError("head_importance must be contiguous fp32 [H]")
+    H = head_importance.numel()
+    if mask is None:
+        mask = torch.empty(H, dtype=torch.uint8, device=head_importance.device)
+    with torch.cuda.device(mask.device):
+        _lib.check(lib.spatten_head_select(head_importance.data_ptr(), H, int(keep_heads), mask.data_ptr(),
+                                           C.c_void_p(_stream_ptr(mask.device))))
+    return mask

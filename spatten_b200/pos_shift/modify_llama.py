@@ -116,7 +116,8 @@ def llama_pos_shift_attention_forward(
                               k_new=k_new.view(bsz, H_kv, D), v_new=v_new.view(bsz, H_kv, D),
                               q_pos=position_ids.reshape(bsz), mask=mask,
                               logits=scores.view(bsz, H, kv_seq_len),
-                              head_mask=getattr(self, "spatten_head_mask", None))
+                              head_mask=getattr(self, "spatten_head_mask", None),
+                              head_importance=getattr(self, "spatten_head_importance", None))
     else:
         # prefill / chunk: store the new K/V rows (:95-100), then score every query row against the cache
         kbuf[:, :, past_len:kv_seq_len].copy_(k_new.transpose(1, 2))
