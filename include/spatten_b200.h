@@ -208,6 +208,49 @@ typedef struct SpattenSparsePvArgs {
 } SpattenSparsePvArgs;
 int spatten_sparse_pv(const SpattenSparsePvArgs* args, void* stream);
 
+/* Progressive quantisation of the KV cache (README.md:11 "KV progressive quantization"; BASELINE config 4).
+ * Per (batch, kv head): K and V each stored as an MSB and an LSB 4-bit plane, u8 [tokens, head_dim/2], of the
+ * offset-128 int8 code u = clamp(rint(x / scale), -127, 127) + 128 (msb = u >> 4, lsb = u & 15), plus one fp16
+ * scale = max|x| / 127 per token (MatrixFetcher.scala:48-51 profiles (4,1)/(8,1); :344-347 MSB left-aligned, LSB
+ * right-aligned).  Nibble order inside every 8-dim group: [d0,d2,d4,d6,d1,d3,d5,d7].  Token capacity of every
+ * buffer must be a multiple of 8.  head_dim == 128 only. */
+typedef struct SpattenQuantKV {
+  void* k_msb; void* k_lsb; void* k_scale;
+  void* v_msb; void* v_lsb; void* v_scale;
+  int64_t plane_stride_b, plane_stride_h;   /* bytes between sequences / kv heads of a plane */
+  int64_t scale_stride_b, scale_stride_h;   /* elements between sequences / kv heads of a scale array */
+} SpattenQuantKV;
+
+/* Quantise `n_tokens` fp16 rows per (batch, kv head) of K and V (strides in elements) into slots
+ * [slot0, slot0 + n_tokens) of the planes: the cache write path that precedes the decode kernel. */
+int spatten_kv_quantize(const void* k, const void* v, int64_t stride_b, int64_t stride_h, int64_t stride_t,
+                        int32_t batch, int32_t num_kv_heads, int32_t n_tokens, int32_t head_dim,
+                        const SpattenQuantKV* dst, int32_t slot0, void* stream);
+
+/* Decode attention over the quantised cache with the RTL's MSB-first / requant-replay control flow:
+ * pass 1 scores with the MSB plane only (bucket mid-points) and runs softmax and P.V; RequantDecision
+ * (RequantDecision.scala:47-72) flags every (batch, head) row whose largest softmax probability is below
+ * `requant_threshold`; pass 2 replays exactly those rows with MSB+LSB keys (SpAttenController.scala:140-175).
+ * Values use the MSB plane (v_bits = 4) or both planes (v_bits = 8).  The query's token must already be in the
+ * cache (spatten_kv_quantize); q_pos NULL = kv_len - 1.  requant_threshold <= 0 skips pass 2. */
+typedef struct SpattenQuantDecodeArgs {
+  uint32_t struct_size;
+  int32_t batch, num_heads, num_kv_heads, head_dim, kv_len, rope_len, v_bits;
+  float requant_threshold;
+  SpattenQuantKV kv;
+  const void* q;            /* fp16 [b, H, D] un-rotated */
+  const void* rope;         /* fp16 [rope_len, D] (as spatten_decode_attn) */
+  const int64_t* q_pos;     /* [b] or NULL */
+  void* out;                /* fp16 [b, H, D] */
+  void* logits;             /* optional fp16 [b*H, logits_stride] */
+  int64_t logits_stride;
+  uint8_t* need_requant;    /* out [b*H]: 1 = row was replayed with the LSB plane */
+  void* workspace;          /* >= spatten_decode_quant_workspace_bytes(...) */
+  size_t workspace_bytes;
+} SpattenQuantDecodeArgs;
+size_t spatten_decode_quant_workspace_bytes(int32_t batch, int32_t num_heads, int32_t head_dim);
+int spatten_decode_attn_quant(const SpattenQuantDecodeArgs* args, void* stream);
+
 /* Head pruning (README.md:21 "head pruning to remove unessential heads"): mask[h] = 1 for the `keep_heads`
  * heads with the largest cumulative importance (fp32 [num_heads], accumulated by spatten_decode_attn's
  * `head_importance` output), ties -> lowest head index; 0 elsewhere.  The mask is what spatten_decode_attn

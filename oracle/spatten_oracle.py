@@ -278,6 +278,26 @@ def head_prune_mask(cum_head_importance: torch.Tensor, keep_heads: int) -> torch
     return mask
 
 
+# nibble position p (bits 4p..4p+3 of each little-endian u32 that covers 8 dims) holds dim _NIB_ORDER[p] of the group
+_NIB_ORDER = [0, 2, 4, 6, 1, 3, 5, 7]
+
+
+def _pack_nibbles(n: torch.Tensor) -> torch.Tensor:
+    """int nibbles [.., D] (dim order) -> u8 [.., D/2] in the plane's fetch order."""
+    *lead, D = n.shape
+    g = n.reshape(*lead, D // 8, 8)[..., _NIB_ORDER]            # now indexed by nibble position
+    return (g[..., 0::2] | (g[..., 1::2] << 4)).reshape(*lead, D // 2).to(torch.uint8)
+
+
+def _unpack_nibbles(p: torch.Tensor) -> torch.Tensor:
+    """u8 [.., D/2] -> int32 nibbles [.., D] in dim order."""
+    *lead, half = p.shape
+    lo, hi = (p & 15).to(torch.int32), (p >> 4).to(torch.int32)
+    pos = torch.stack((lo, hi), dim=-1).reshape(*lead, half // 4, 8)       # nibble positions 0..7 of each group
+    inv = [_NIB_ORDER.index(d) for d in range(8)]
+    return pos[..., inv].reshape(*lead, half * 2)
+
+
 def quantize_kv_planes(x: torch.Tensor):
     """fp16 [.., S, D] -> (msb u8 [.., S, D/2], lsb u8 [.., S, D/2], scale fp16 [.., S]).
 
@@ -285,7 +305,8 @@ def quantize_kv_planes(x: torch.Tensor):
     (fp16-rounded), stored as an unsigned byte u = q + 128 split MSB-first into two 4-bit planes:
     msb = u >> 4, lsb = u & 15 (MatrixFetcher.scala:48-51 profiles (4,1)/(8,1); MSB fetch
     left-aligned :344-345, LSB refetch right-aligned :346-347; masked low-4-bit write
-    SpAttenController.scala:230-232).  Two nibbles per byte, low nibble = even d.
+    SpAttenController.scala:230-232).  Nibble order inside every 8-dim group is [d0,d2,d4,d6,d1,d3,d5,d7]
+    (a fetch-friendly interleave, cf. the RTL's bit-reversed layout BMR.scala:59-65).
     MSB-only dequant uses the bucket midpoint: x ~ ((msb<<4 | 8) - 128) * scale.
     Self-consistent, not reference-pinned.
     """
@@ -294,21 +315,20 @@ def quantize_kv_planes(x: torch.Tensor):
     scale = (amax / 127.0).to(torch.float16)
     sf = scale.float().clamp_min(1e-8)
     q = torch.clamp(torch.round(xf / sf[..., None]), -127, 127).to(torch.int32)
-    u = (q + 128).to(torch.uint8)
-    msb_n, lsb_n = u >> 4, u & 15
-    msb = (msb_n[..., 0::2] | (msb_n[..., 1::2] << 4)).to(torch.uint8)
-    lsb = (lsb_n[..., 0::2] | (lsb_n[..., 1::2] << 4)).to(torch.uint8)
-    return msb, lsb, scale
+    u = q + 128
+    return _pack_nibbles(u >> 4), _pack_nibbles(u & 15), scale
+
+
+def dequant_ints(msb: torch.Tensor, lsb: Optional[torch.Tensor]) -> torch.Tensor:
+    """Planes -> the signed integer code [.., S, D] (int32): 16*m + l - 128, l = 8 (mid-point) without the LSB plane."""
+    m = _unpack_nibbles(msb)
+    l = _unpack_nibbles(lsb) if lsb is not None else torch.full_like(m, 8)
+    return m * 16 + l - 128
 
 
 def dequant_planes(msb: torch.Tensor, lsb: Optional[torch.Tensor], scale: torch.Tensor) -> torch.Tensor:
     """Inverse of quantize_kv_planes -> fp32 [.., S, D].  lsb=None => MSB-only (midpoint) dequant."""
-    def unpack(p):
-        lo, hi = (p & 15).to(torch.int32), (p >> 4).to(torch.int32)
-        return torch.stack((lo, hi), dim=-1).flatten(-2)
-    m = unpack(msb)
-    l = unpack(lsb) if lsb is not None else torch.full_like(m, 8)
-    return ((m * 16 + l) - 128).float() * scale.float()[..., None]
+    return dequant_ints(msb, lsb).float() * scale.float()[..., None]
 
 
 def requant_decision(max_prob: torch.Tensor, threshold: float) -> torch.Tensor:
@@ -322,24 +342,29 @@ def attn_core_quantized(q_rot, k_msb, k_lsb, k_scale, v_msb, v_lsb, v_scale, rop
 
     Pass 1 scores with MSB-only keys; if the largest softmax probability of the row is below
     `threshold` (flat distribution => quantisation error matters, RequantDecision.scala:72) the row
-    refetches the LSB plane and rescoring uses full 8-bit keys (SpAttenController.scala:140-175
-    replay).  Keys are stored un-rotated; RoPE is applied to the dequantised key in fp32.
+    refetches the LSB plane and rescoring uses full 8-bit keys (SpAttenController.scala:140-175 replay);
+    a replayed row recomputes its output from the 8-bit logits.
+    Keys are stored un-rotated; RoPE is applied to the integer code (exact in fp16) with the same fp16
+    op sequence as the fp16 path (modify_llama.py:27), the dot with the rotated query accumulates in fp32
+    and is multiplied by the token's scale, then rounded to fp16 and divided by sqrt(D) like :111-113.
     Values use the MSB plane only (v_bits=4) or both planes (v_bits=8).
+    rope_cos / rope_sin: fp16 [S, D] (HF tables).
     Returns (out fp16 [b,H,1,D], logits fp16 [b,H,1,S], need_requant bool [b,H]).
     Self-consistent, not reference-pinned.
     """
     D = q_rot.shape[-1]
-    cos, sin = rope_cos.float(), rope_sin.float()           # [S, D]
+    cos, sin = rope_cos.to(torch.float16), rope_sin.to(torch.float16)
 
-    def scores(k_deq):
-        kr = k_deq * cos + rotate_half(k_deq) * sin
-        s = torch.einsum("bhd,bhsd->bhs", q_rot[:, :, 0, :].float(), kr)
+    def scores(k_int):
+        kh = k_int.to(torch.float16)                                       # exact: |code| <= 128
+        kr = (kh * cos) + (rotate_half(kh) * sin)                          # fp16, rounded after every op
+        s = torch.einsum("bhd,bhsd->bhs", q_rot[:, :, 0, :].float(), kr.float()) * k_scale.float()
         return (s.to(torch.float16).float() / math.sqrt(D)).to(torch.float16)
 
-    s1 = scores(dequant_planes(k_msb, None, k_scale))
+    s1 = scores(dequant_ints(k_msb, None))
     p1 = torch.softmax(s1.float(), dim=-1)
-    need = requant_decision(p1.amax(dim=-1), threshold)
-    s2 = scores(dequant_planes(k_msb, k_lsb, k_scale))
+    need = requant_decision(p1.amax(dim=-1), threshold) if threshold > 0 else torch.zeros_like(p1[..., 0], dtype=torch.bool)
+    s2 = scores(dequant_ints(k_msb, k_lsb))
     logits = torch.where(need[..., None], s2, s1)
     p = torch.softmax(logits.float(), dim=-1)
     vd = dequant_planes(v_msb, v_lsb if v_bits == 8 else None, v_scale)

@@ -78,6 +78,29 @@ class SparsePvArgs(C.Structure):
     ]
 
 
+class QuantKV(C.Structure):
+    """Mirror of `SpattenQuantKV`."""
+    _fields_ = [
+        ("k_msb", C.c_void_p), ("k_lsb", C.c_void_p), ("k_scale", C.c_void_p),
+        ("v_msb", C.c_void_p), ("v_lsb", C.c_void_p), ("v_scale", C.c_void_p),
+        ("plane_stride_b", C.c_int64), ("plane_stride_h", C.c_int64),
+        ("scale_stride_b", C.c_int64), ("scale_stride_h", C.c_int64),
+    ]
+
+
+class QuantDecodeArgs(C.Structure):
+    """Mirror of `SpattenQuantDecodeArgs`."""
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("batch", C.c_int32), ("num_heads", C.c_int32), ("num_kv_heads", C.c_int32),
+        ("head_dim", C.c_int32), ("kv_len", C.c_int32), ("rope_len", C.c_int32), ("v_bits", C.c_int32),
+        ("requant_threshold", C.c_float),
+        ("kv", QuantKV),
+        ("q", C.c_void_p), ("rope", C.c_void_p), ("q_pos", C.c_void_p), ("out", C.c_void_p),
+        ("logits", C.c_void_p), ("logits_stride", C.c_int64), ("need_requant", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 DTYPE_F16, DTYPE_F32 = 0, 1
 
 _lib = None
@@ -116,6 +139,11 @@ def _bind_optional(lib):
     lib.spatten_topk_select.argtypes = [C.POINTER(SelectArgs), C.c_void_p]
     lib.spatten_kv_gather.argtypes = [C.POINTER(GatherArgs), C.c_void_p]
     lib.spatten_sparse_pv.argtypes = [C.POINTER(SparsePvArgs), C.c_void_p]
+    lib.spatten_kv_quantize.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+                                        C.c_int32, C.c_int32, C.POINTER(QuantKV), C.c_int32, C.c_void_p]
+    lib.spatten_decode_quant_workspace_bytes.restype = C.c_size_t
+    lib.spatten_decode_quant_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    lib.spatten_decode_attn_quant.argtypes = [C.POINTER(QuantDecodeArgs), C.c_void_p]
     lib.spatten_head_select.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
 
 

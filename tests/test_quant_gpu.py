@@ -1,0 +1,74 @@
+"""GPU checks of the progressive-quantisation path (parity unpinned: vs the self-consistent oracle restatement)."""
+import pytest
+import torch
+
+from detgen import det_normal
+from helpers import rel_err
+from oracle import spatten_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(b, H, D, n, seed):
+    q = det_normal((b, H, 1, D), seed, 1.0, torch.float16)
+    k = det_normal((b, H, n, D), seed + 1, 1.0, torch.float16)
+    v = det_normal((b, H, n, D), seed + 2, 1.0, torch.float16)
+    return q, k, v
+
+
+@pytest.mark.parametrize("b,H,n", [(1, 4, 100), (2, 8, 1000), (1, 32, 8192)])
+def test_quantize_planes_bit_exact(b, H, n):
+    from spatten_b200.quant_kv import QuantKVCache
+    _, k, v = _setup(b, H, 128, n, 500 + n)
+    cache = QuantKVCache(b, H, n + 5)
+    cache.append(k[:, :, : n // 2].cuda(), v[:, :, : n // 2].cuda())
+    cache.append(k[:, :, n // 2:].cuda(), v[:, :, n // 2:].cuda())          # second append lands at slot n//2
+    assert cache.length == n
+    for t, (msb, lsb, sc) in ((k, (cache.k_msb, cache.k_lsb, cache.k_scale)), (v, (cache.v_msb, cache.v_lsb, cache.v_scale))):
+        rm, rl, rs = O.quantize_kv_planes(t)
+        assert torch.equal(sc.cpu()[:, :, :n], rs)
+        assert torch.equal(msb.cpu()[:, :, :n], rm) and torch.equal(lsb.cpu()[:, :, :n], rl)
+
+
+@pytest.mark.parametrize("b,H,n,thr,v_bits", [
+    (1, 8, 300, 0.0, 4),          # no requant: MSB-only keys and values
+    (1, 8, 300, 1.1, 4),          # every row replays with the LSB plane
+    (2, 4, 1000, 0.02, 8),        # mixed decision, 8-bit values
+    (1, 32, 8192, 0.004, 4),      # BASELINE config 4 shape (one layer): 16K pruned to 8K tokens
+])
+def test_quant_decode_matches_oracle(b, H, n, thr, v_bits):
+    from spatten_b200 import ops
+    from spatten_b200.quant_kv import QuantKVCache
+    D = 128
+    q, k, v = _setup(b, H, D, n, 900 + n)
+    if thr == 0.02:                                   # sharpen half of the rows so the decision really is mixed
+        k[:, ::2, n // 3] = q[:, ::2, 0] * 3
+    km, kl, ks = O.quantize_kv_planes(k)
+    vm, vl, vs = O.quantize_kv_planes(v)
+    cos, sin = O.rotary_tables(D, n, torch.float16)
+    pos = torch.full((b, 1), n - 1, dtype=torch.int64)
+    q_rot = O.rope_single(q, cos, sin, pos)
+    ref_out, ref_logits, ref_need = O.attn_core_quantized(q_rot, km, kl, ks, vm, vl, vs, cos[0, 0], sin[0, 0], thr, v_bits)
+
+    cache = QuantKVCache(b, H, n)
+    cache.append(k.cuda(), v.cuda())
+    logits = torch.empty((b, H, n), dtype=torch.float16, device="cuda")
+    out, need = cache.decode(q[:, :, 0].cuda(), ops.rope_table(D, n, "cuda"), threshold=thr, v_bits=v_bits, logits=logits)
+    torch.cuda.synchronize()
+    need = need.cpu().view(b, H).bool()
+    # the decision compares 1/L with the threshold: identical unless a row sits within rounding of it
+    p1max = torch.softmax(O.attn_core_quantized(q_rot, km, kl, ks, vm, vl, vs, cos[0, 0], sin[0, 0], 0.0, v_bits)[1].float(), -1).amax(-1)[:, :, 0]
+    decided = (p1max - thr).abs() > 1e-3 * max(thr, 1e-6)
+    assert torch.equal(need[decided], ref_need[decided])
+    if thr == 0.02:
+        assert need.any() and not need.all()
+    agree = need == ref_need
+    # unpinned path: the oracle's fp32 einsum and the kernel's lane-tree sum differ in order, and the result is then
+    # scaled, rounded to fp16, divided and rounded again -- allow two ulps of the intermediate, require ~all identical
+    a, r = logits.cpu()[agree].float(), ref_logits[:, :, 0][agree].float()
+    assert ((a - r).abs() <= 4e-3 * r.abs() + 2e-4).all()
+    assert (a == r).float().mean() > 0.99
+    assert rel_err(out.cpu()[agree], ref_out[:, :, 0][agree]) <= 2e-3
+    # quantisation itself is the dominant error vs the fp16 attention: sanity bound only
+    full, _, _ = O.attn_forward_core(q, k[:, :, -1:], v[:, :, -1:], k[:, :, :-1], v[:, :, :-1], pos, None)
+    assert rel_err(out.cpu(), full[:, :, 0]) < (0.25 if v_bits == 4 else 0.1)
