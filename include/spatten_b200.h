@@ -66,6 +66,10 @@ int spatten_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * appended).  First step of the RTL-ordered path DotProduct -> TopK -> MultiplyValue over survivors
  * (SpAttenController.scala:347,588,668-749); see spatten_sparse_pv. */
 #define SPATTEN_DECODE_SCORES_ONLY 8u
+/* Use the 8-token-tile build (96 KiB shared memory, <= 128 registers: two CTAs per SM) instead of the default
+ * 16-token tiles (192 KiB, one CTA per SM).  Opt-in: on B200 the co-resident CTAs of consecutive PDL launches were
+ * measured to compete more than they overlap. */
+#define SPATTEN_DECODE_SMALL_TILES 16u
 
 typedef struct SpattenDecodeArgs {
   uint32_t struct_size;   /* = sizeof(SpattenDecodeArgs), ABI guard */

@@ -31,9 +31,12 @@ namespace spatten {
 
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
-constexpr int kPasses = 4;    // a pass = 4 keys x 8 lanes; passes of one tile are independent (ILP)
-constexpr int kTile = 4 * kPasses;  // tokens per pipeline stage (per warp)
-constexpr int kStages = 3;    // ring depth per warp -> 8 warps * 3 * 8 KiB = 192 KiB in flight per SM (D=128)
+// A pass = 4 keys x 8 lanes; the passes of one tile are independent (ILP).  Two tile shapes are built:
+//   P = 4: 16-token tiles, 3 stages -> 8 warps * 3 * 8 KiB = 192 KiB in flight per SM, one CTA per SM;
+//   P = 2:  8-token tiles, 3 stages -> 96 KiB per CTA and <= 128 registers, so TWO CTAs fit on an SM: with
+//           programmatic dependent launch the next layer's kernel becomes resident beside this one and its
+//           preamble + first K/V tiles overlap this kernel's merge tail.
+constexpr int kStages = 3;
 constexpr int kMaxPartials = 8192;  // (row, split) partial records the workspace holds
 constexpr int kMaxSplits = 256;     // splits per row the merge handles
 constexpr int kMaxClusterSize = 8;  // CTAs per cluster in cluster mode: 8 (portable maximum) or 4
@@ -68,6 +71,7 @@ struct DecodeParams {
   int pdl;                 // launched with programmatic stream serialization (SPATTEN_DECODE_PDL)
   int scores_only;         // SPATTEN_DECODE_SCORES_ONLY: stream K only, export logits, no softmax / P.V / out
   int ds_shift;            // cluster mode: log2(D * rpc / cluster)
+  int passes;              // tile shape: 4 (16-token tiles, 1 CTA/SM) or 2 (8-token tiles, 2 CTAs/SM)
   int cluster;             // 0: global partials + per-row tickets; 4 or 8: every split of a row lives in one
                            // thread-block cluster of that size and partials are merged through distributed shared memory
   unsigned long long* dbg;  // optional [grid][8 warps][8] globaltimer stamps (tools/microbench.py --timeline)
@@ -103,8 +107,9 @@ __device__ __forceinline__ float div_by_const(float x, float c, float rc) {
   return (fabsf(y2) <= 3.4028234e38f) ? y2 : y;
 }
 
-template <int D, int MODE, bool DBG>   // MODE 0: global partials + tickets (or one split); MODE 1: cluster / DSMEM merge
-__global__ void __launch_bounds__(kThreads, 1) decode_attn_kernel(const DecodeParams p) {
+template <int D, int MODE, bool DBG, int kPasses>   // MODE 0: global partials + tickets (or one split); MODE 1: cluster / DSMEM merge
+__global__ void __launch_bounds__(kThreads, kPasses == 2 ? 2 : 1) decode_attn_kernel(const DecodeParams p) {
+  constexpr int kTile = 4 * kPasses;  // tokens per pipeline stage (per warp)
   constexpr int E2 = D / 16;   // halves per lane in each half of the row (8 lanes cover D/2)
   constexpr int NH2 = E2 / 2;  // half2 per lane per half-row
   constexpr int VB = E2 * 2;   // bytes per lane per half-row: 16 (D=128) or 8 (D=64)
@@ -544,7 +549,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_attn_kernel(const DecodePa
     const float2* ml = p.part_ml + static_cast<int64_t>(row) * p.n_splits;
     constexpr int PER = D / 32;   // output dims per lane: 4 (D=128) or 2 (D=64)
     using PV_t = typename VecT<PER * 4>::type;
-    constexpr int kU = 40;        // partial loads in flight per lane: one batch covers the usual <= 40 splits
+    // partial loads in flight per lane: one batch covers the usual <= 40 splits (the 128-register build takes two)
+    constexpr int kU = kPasses == 2 ? 20 : 40;
     PV_t v[kU];
     // everything the merge needs is requested at once: the (m, l) pairs and the first batch of partials
     float2 mls[kMaxSplits / 32];
@@ -645,27 +651,28 @@ static void choose_split(int rows, int n_total, int sms, int& rpc, int& spc, int
 // K/V rings + mbarriers + (cluster mode) the receive buffer for pushed partials: n_splits * (DS + 2) floats with
 // n_splits * DS == 8 * D and n_splits <= 64
 template <int D>
-constexpr size_t decode_smem_bytes() {
-  return static_cast<size_t>(kWarps) * kStages * 2 * kTile * D * 2 + kWarps * kStages * 8 +
+constexpr size_t decode_smem_bytes(int passes) {
+  return static_cast<size_t>(kWarps) * kStages * 2 * (4 * passes) * D * 2 + kWarps * kStages * 8 +
          (static_cast<size_t>(kWarps) * D + 2 * 64) * sizeof(float);
 }
 
 using DecodeKernel = void (*)(const DecodeParams);
 
 template <int D>
-static DecodeKernel decode_kernel(int mode, bool dbg) {
-  if (D == 128 && dbg) return mode ? decode_attn_kernel<128, 1, true> : decode_attn_kernel<128, 0, true>;
-  return mode ? decode_attn_kernel<D, 1, false> : decode_attn_kernel<D, 0, false>;
+static DecodeKernel decode_kernel(int mode, bool dbg, int passes) {
+  if (passes == 2) return mode ? decode_attn_kernel<D, 1, false, 2> : decode_attn_kernel<D, 0, false, 2>;
+  if (D == 128 && dbg) return mode ? decode_attn_kernel<128, 1, true, 4> : decode_attn_kernel<128, 0, true, 4>;
+  return mode ? decode_attn_kernel<D, 1, false, 4> : decode_attn_kernel<D, 0, false, 4>;
 }
 
 template <int D>
-static int configure_decode(DecodeKernel k, int slot) {
-  static bool configured[64][4] = {};
+static int configure_decode(DecodeKernel k, int slot, int passes) {
+  static bool configured[64][8] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && !configured[dev][slot]) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(decode_smem_bytes<D>()));
+                                         static_cast<int>(decode_smem_bytes<D>(passes)));
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(decode_attn_kernel)");
     configured[dev][slot] = true;
   }
@@ -679,12 +686,12 @@ static int max_active_clusters(int cs) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && cached[dev][cs] != 0) return cached[dev][cs];
-  DecodeKernel k = decode_kernel<D>(1, false);
-  if (configure_decode<D>(k, 1) != SPATTEN_OK) return 0;
+  DecodeKernel k = decode_kernel<D>(1, false, 4);
+  if (configure_decode<D>(k, 1, 4) != SPATTEN_OK) return 0;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(cs * 64);
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = decode_smem_bytes<D>();
+  cfg.dynamicSmemBytes = decode_smem_bytes<D>(4);
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cs;
@@ -700,11 +707,11 @@ static int max_active_clusters(int cs) {
 
 template <int D>
 static int launch_decode(const DecodeParams& p, cudaStream_t st) {
-  constexpr size_t smem = decode_smem_bytes<D>();
-  const bool dbg = p.dbg != nullptr && D == 128;
+  const bool dbg = p.dbg != nullptr && D == 128 && p.passes == 4;
   const int mode = p.cluster ? 1 : 0;
-  DecodeKernel k = decode_kernel<D>(mode, dbg);
-  if (int rc = configure_decode<D>(k, mode + (dbg ? 2 : 0))) return rc;
+  const size_t smem = decode_smem_bytes<D>(p.passes);
+  DecodeKernel k = decode_kernel<D>(mode, dbg, p.passes);
+  if (int rc = configure_decode<D>(k, mode + (dbg ? 2 : 0) + (p.passes == 2 ? 4 : 0), p.passes)) return rc;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(p.cluster ? p.n_rg * p.cluster : p.n_rg * p.n_ranges);
   cfg.blockDim = dim3(kThreads);
@@ -860,6 +867,9 @@ extern "C" int spatten_decode_attn(const SpattenDecodeArgs* a, void* stream) {
     }
   }
   p.tok_per_split = (std::max(a->kv_len, 1) + p.n_splits - 1) / p.n_splits;
+  // The small-footprint build is opt-in: measured on B200 (profiles/r1_microbench_decode_v11.jsonl) two co-resident
+  // CTAs of consecutive PDL launches compete more than they overlap (config 2: 14.5 us vs 10.5 us per layer).
+  p.passes = (a->flags & SPATTEN_DECODE_SMALL_TILES) ? 2 : 4;
   if (p.n_splits > 1 && !p.cluster) {
     const size_t need = spatten_decode_workspace_bytes(a->batch, a->num_heads, a->head_dim);
     if (a->workspace == nullptr || a->workspace_bytes < need) {

@@ -114,16 +114,18 @@ def test_cluster_and_ticket_variants_agree(b, H, D, past):
     pos = torch.full((b, 1), past, dtype=torch.int64)
     ref_out, ref_scores, _ = O.attn_forward_core(q, k, v, pk, pv, pos, None)
     res = {}
-    for name, fl in (("cluster", 0), ("ticket", _lib.DECODE_NO_CLUSTER)):
+    for name, fl in (("cluster", 0), ("ticket", _lib.DECODE_NO_CLUSTER), ("cluster_small", _lib.DECODE_SMALL_TILES),
+                     ("ticket_small", _lib.DECODE_NO_CLUSTER | _lib.DECODE_SMALL_TILES)):
         out, logits, kc, vc, imp, himp = run_kernel(q, k, v, pk, pv, pos, None, want_importance=True, flags=fl)
         assert_logits_close(logits, ref_scores[:, :, 0, :], name)
         assert rel_err(out, ref_out[:, :, 0, :]) <= OUT_REL_TOL, name
         assert torch.equal(kc[:, :, past], k[:, :, 0]) and torch.equal(vc[:, :, past], v[:, :, 0])
         res[name] = (out, logits, imp.cpu(), himp.cpu())
-    assert torch.equal(res["cluster"][1], res["ticket"][1])                     # logits: bit-identical
-    assert rel_err(res["cluster"][0], res["ticket"][0]) <= 1e-3
-    assert torch.allclose(res["cluster"][2], res["ticket"][2], rtol=1e-3, atol=1e-7)
-    assert torch.allclose(res["cluster"][3], res["ticket"][3], rtol=1e-3, atol=1e-3)
+    for other in ("ticket", "cluster_small", "ticket_small"):
+        assert torch.equal(res["cluster"][1], res[other][1]), other                # logits: bit-identical
+        assert rel_err(res["cluster"][0], res[other][0]) <= 1e-3, other
+        assert torch.allclose(res["cluster"][2], res[other][2], rtol=1e-3, atol=1e-7), other
+        assert torch.allclose(res["cluster"][3], res[other][3], rtol=1e-3, atol=1e-3), other
 
 
 def test_decode_head_mask_and_noappend():

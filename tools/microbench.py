@@ -56,6 +56,72 @@ def bench_shape(b, H, D, n, L, iters, logits_on=True, graph=True, flags=0):
             "frac_6445": round(bytes_layer / us_layer / 1e3 / 6445, 4)}
 
 
+def _time_graph(fn, iters):
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            fn()
+        s.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=s):
+            fn()
+        for _ in range(3):
+            gr.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.synchronize()
+        e0.record(s)
+        for _ in range(iters):
+            gr.replay()
+        e1.record(s)
+        s.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def bench_extra(iters):
+    """Config-4 (int4 planes, 16K -> 8K tokens) and the RTL-ordered local-V path, one layer-step each, L layers cycled."""
+    from spatten_b200.quant_kv import QuantKVCache
+    dev, b, H, D, n, L = "cuda", 1, 32, 128, 8192, 16
+    g = torch.Generator(device=dev).manual_seed(3)
+    rope = ops.rope_table(D, n + 8, dev)
+    caches = []
+    for l in range(L):
+        c = QuantKVCache(b, H, n)
+        c.append(torch.randn((b, H, n, D), generator=g, device=dev, dtype=torch.float16),
+                 torch.randn((b, H, n, D), generator=g, device=dev, dtype=torch.float16))
+        caches.append(c)
+    q = torch.randn((L, b, H, D), generator=g, device=dev, dtype=torch.float16)
+    logits = torch.empty((L, b, H, n), device=dev, dtype=torch.float16)
+    for thr, vb in ((0.0, 4), (1e-4, 4), (1.1, 4), (0.0, 8)):
+        needs = []
+
+        def step():
+            needs.clear()
+            for l in range(L):
+                needs.append(caches[l].decode(q[l], rope, threshold=thr, v_bits=vb, logits=logits[l])[1])
+        ms = _time_graph(step, iters)
+        r = float(torch.stack(needs).float().mean())
+        kb = n * H * (D // 2) * (1 + r) + n * H * (D // 2) * (vb // 4) + 2 * n * H * 2      # K msb(+lsb on replay) + V + scales
+        us = ms * 1e3 / L
+        print(json.dumps({"kind": "quant_c4", "b": b, "H": H, "n": n, "thr": thr, "v_bits": vb, "requant_frac": round(r, 3),
+                          "us_per_layer": round(us, 2), "alg_MiB": round(kb / 2**20, 2), "GBps": round(kb / us / 1e3, 1),
+                          "frac_6445": round(kb / us / 1e3 / 6445, 4)}), flush=True)
+    # local V: score all 4096 keys, multiply the top 2048 values (Mode B, 48 MiB/layer at config-2 scale)
+    n, keep = 4096, 2048
+    kc = [torch.randn((b, H, n, D), generator=g, device=dev, dtype=torch.float16) for _ in range(L)]
+    vc = [torch.randn((b, H, n, D), generator=g, device=dev, dtype=torch.float16) for _ in range(L)]
+    rope = ops.rope_table(D, n + 8, dev)
+
+    def step_b():
+        for l in range(L):
+            ops.local_v_attn(q[l], kc[l], vc[l], n, rope, keep)
+    ms = _time_graph(step_b, iters)
+    kb = b * H * (n + keep) * D * 2
+    us = ms * 1e3 / L
+    print(json.dumps({"kind": "local_v_modeB", "b": b, "H": H, "n": n, "keep_v": keep, "us_per_layer": round(us, 2),
+                      "alg_MiB": round(kb / 2**20, 2), "GBps": round(kb / us / 1e3, 1),
+                      "frac_6445": round(kb / us / 1e3 / 6445, 4)}), flush=True)
+
+
 def timeline(b, H, D, n, L, flags=0):
     """Phase timeline of the LAST of L back-to-back launches (warm caches), from %globaltimer stamps."""
     import ctypes as C
@@ -104,7 +170,11 @@ if __name__ == "__main__":
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--timeline", action="store_true", help="dump per-phase globaltimer stamps for one launch")
     ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--extra", action="store_true", help="config-4 quantised decode and Mode-B local-V timings")
     a = ap.parse_args()
+    if a.extra:
+        bench_extra(a.iters)
+        sys.exit(0)
     if a.timeline:
         timeline(*map(int, (a.shape or "1,32,128,2048,32").split(",")), flags=a.flags)
         sys.exit(0)
@@ -115,6 +185,6 @@ if __name__ == "__main__":
     shapes = [(1, 32, 128, 2048, 32), (1, 32, 128, 4096, 32), (1, 32, 128, 8192, 16), (8, 5, 128, 16384, 8),
               (1, 4, 128, 2048, 32), (1, 32, 128, 512, 32)]
     for (b, H, D, n, L) in shapes:
-        for fl in (0, 3, 4, 7):
+        for fl in (0, 3, 7, 19, 23):
             print(json.dumps(bench_shape(b, H, D, n, L, a.iters, True, flags=fl)), flush=True)
     print(json.dumps(bench_shape(1, 32, 128, 2048, 32, a.iters, True, graph=False)), flush=True)
