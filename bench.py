@@ -234,10 +234,23 @@ def run_ours(args):
     def attn_layer(l):
         _lib.check(lib.spatten_decode_attn(C.byref(layer_args[l]), sptr))
 
-    from spatten_b200.parallel import HeadShard, exchange_heads
+    from spatten_b200.parallel import HeadShard, PeerExchange, exchange_heads
     shard = HeadShard(rank, world, H)
+    px = None
+    if world > 1 and args.collective == "fused":
+        # attention output stored straight into every peer's gather buffer by the kernel; no collective kernel
+        px = PeerExchange(L, shard, b, D, dev)
+        gathered = px.gathered
+        for l in range(L):
+            # layer l waits, inside its own kernel, for layer l-1's exchange; one wait launch closes the step
+            px.fill_args(layer_args[l], l, wait_on_layer=(l - 1) if l > 0 else None)
+            layer_args[l].flags = _lib.DECODE_PDL | _lib.DECODE_PDL_KV_STABLE
 
     def collective(l):
+        if px is not None:
+            if l == L - 1:
+                px.wait(l, stream.cuda_stream)      # last layer: all N producers have stored their heads
+            return
         # zero-padded all-reduce (re-zeroes the peers' slots first) or all-gather of the per-rank head blocks
         exchange_heads(gathered[l], shard, args.collective)
 
@@ -429,7 +442,10 @@ def run_ours(args):
             "config": workload_config(world, b),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": L * args.steps, "cuda_graph": graphed,
-            "collective": None if world == 1 else f"nccl {args.collective} of [N={world}, b={b}, H/N={Hl}, D={D}] fp16 per layer",
+            "collective": None if world == 1 else (
+                f"fused: spatten_decode_attn stores [b={b}, H/N={Hl}, D={D}] fp16 into all {world} peers over NVLink + flag wait, per layer"
+                if px is not None else f"nccl {args.collective} of [N={world}, b={b}, H/N={Hl}, D={D}] fp16 per layer"),
+            "peer_wait_timed_out": px.timed_out() if px is not None else None,
             "pdl": bool(flags),
         }
         line.update(extras)
@@ -450,7 +466,8 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--collective", choices=["allreduce", "allgather"], default="allreduce")
+    ap.add_argument("--collective", choices=["fused", "allreduce", "allgather"], default="fused",
+                    help="exchange of the attention output at N>1: in-kernel peer stores + flag wait (fused), or NCCL")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--min-warm-s", type=float, default=0.6,
                     help="keep warming up until this many seconds have run under load (clock sampling); 0 under ncu")

@@ -111,6 +111,24 @@ typedef struct SpattenDecodeArgs {
   int64_t importance_stride;
   float* head_importance; /* optional fp32 [H]: += sum_d |out[b,h,d]| (head importance) */
 
+  /* Fused exchange for head sharding (n_peers > 0): the output rows are stored into every peer GPU's gather
+   * buffer over NVLink (peer_out[r] = address, mapped in THIS process, of this rank's slot in rank r's buffer;
+   * the list includes the rank itself) instead of `out`, and when the whole grid has finished, one flag word per
+   * peer (peer_flags[r], in rank r's memory) is incremented with system-scope release.  The consumer calls
+   * spatten_wait_flags.  No separate collective kernel runs. */
+  int32_t n_peers;        /* 0 = write `out` only */
+  void* peer_out[8];
+  void* peer_flags[8];
+  void* done_counter;     /* local u32, zero-initialised once (self-resetting) */
+  /* Consumer side folded into the kernel (needs n_peers > 0): after its K/V prefetch is in flight and before it
+   * reads q, every warp waits until the wait_n local flag words at wait_flags (the PREVIOUS layer's exchange, one
+   * word per producing rank) have reached *wait_expected + 1; the kernel increments *wait_expected when it is
+   * done.  Saves the separate spatten_wait_flags launch between layers. */
+  int32_t wait_n;
+  const void* wait_flags;
+  void* wait_expected;    /* local u32 call counter, zero-initialised once */
+  void* wait_timeout;     /* local u32, set to 1 if a peer never reports (~2 s) */
+
   void* workspace;        /* >= spatten_decode_workspace_bytes(...) bytes, zero-filled ONCE by the caller
                              before first use (the kernel restores its counters to zero) */
   size_t workspace_bytes;
@@ -118,6 +136,12 @@ typedef struct SpattenDecodeArgs {
 
 size_t spatten_decode_workspace_bytes(int32_t batch, int32_t num_heads, int32_t head_dim);
 int spatten_decode_attn(const SpattenDecodeArgs* args, void* stream);
+
+/* Consumer side of the fused exchange: block the stream until each of the n flag words (one per producing rank,
+ * in local memory) has been incremented once more than at the previous call.  `expected_counter` is a local u32
+ * (zero-initialised once) that counts calls, so the wait is CUDA-graph replayable; `timeout_flag` (u32) is set
+ * to 1 if a peer does not show up within ~2 s (the kernel then returns instead of wedging the GPU). */
+int spatten_wait_flags(const void* flags, int32_t n, void* expected_counter, void* timeout_flag, void* stream);
 
 /* The same step with HOST buffers for the per-step tensors (what a caller that lives on the CPU side of an
  * FFI hands over): q_host / k_new_host / v_new_host are copied into the device staging buffers args->q /

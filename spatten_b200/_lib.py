@@ -41,6 +41,9 @@ class DecodeArgs(C.Structure):
         ("out", C.c_void_p), ("logits", C.c_void_p), ("logits_stride", C.c_int64),
         ("logits_stride_b", C.c_int64), ("logits_stride_q", C.c_int64),
         ("importance", C.c_void_p), ("importance_stride", C.c_int64), ("head_importance", C.c_void_p),
+        ("n_peers", C.c_int32), ("peer_out", C.c_void_p * 8), ("peer_flags", C.c_void_p * 8),
+        ("done_counter", C.c_void_p),
+        ("wait_n", C.c_int32), ("wait_flags", C.c_void_p), ("wait_expected", C.c_void_p), ("wait_timeout", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
@@ -140,6 +143,7 @@ def _bind_optional(lib):
     lib.spatten_topk_select.argtypes = [C.POINTER(SelectArgs), C.c_void_p]
     lib.spatten_kv_gather.argtypes = [C.POINTER(GatherArgs), C.c_void_p]
     lib.spatten_sparse_pv.argtypes = [C.POINTER(SparsePvArgs), C.c_void_p]
+    lib.spatten_wait_flags.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.spatten_kv_quantize.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                         C.c_int32, C.c_int32, C.POINTER(QuantKV), C.c_int32, C.c_void_p]
     lib.spatten_decode_quant_workspace_bytes.restype = C.c_size_t

@@ -39,6 +39,7 @@ constexpr int kThreads = kWarps * 32;
 constexpr int kStages = 3;
 constexpr int kMaxPartials = 8192;  // (row, split) partial records the workspace holds
 constexpr int kMaxSplits = 256;     // splits per row the merge handles
+constexpr int kMaxPeers = 8;        // GPUs of one NVSwitch domain that can receive the fused output exchange
 constexpr int kMaxClusterSize = 8;  // CTAs per cluster in cluster mode: 8 (portable maximum) or 4
 constexpr size_t kTicketBytes = static_cast<size_t>(kMaxPartials) * sizeof(unsigned int);  // per-row tickets
 constexpr float kLog2e = 1.4426950408889634f;
@@ -70,6 +71,17 @@ struct DecodeParams {
   float sqrt_d, rsqrt_d;
   int pdl;                 // launched with programmatic stream serialization (SPATTEN_DECODE_PDL)
   int scores_only;         // SPATTEN_DECODE_SCORES_ONLY: stream K only, export logits, no softmax / P.V / out
+  // Fused exchange (head sharding): the attention output is stored straight into every peer GPU's gather buffer
+  // (P2P over NVLink) instead of `out`; the last warp to finish bumps one flag word on every peer.
+  __half* peer_out[kMaxPeers];
+  unsigned int* peer_flag[kMaxPeers];
+  const unsigned int* wait_flags;   // optional: before reading q, wait until these wait_n local flag words (one per
+  unsigned int* wait_expected;      // producing rank) reached *wait_expected + 1 -- the previous layer's exchange
+  unsigned int* wait_timeout;
+  int wait_n;
+  unsigned int* done;      // local completion counter (self-resetting)
+  unsigned int done_target;
+  int n_peers;
   int ds_shift;            // cluster mode: log2(D * rpc / cluster)
   int passes;              // tile shape: 4 (16-token tiles, 1 CTA/SM) or 2 (8-token tiles, 2 CTAs/SM)
   int cluster;             // 0: global partials + per-row tickets; 4 or 8: every split of a row lives in one
@@ -90,6 +102,34 @@ __device__ __forceinline__ void st_dsmem(float* local, unsigned cta, float v) {
   unsigned raddr;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(local)), "r"(cta));
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(v) : "memory");
+}
+
+// Store one piece of the attention output: locally, or -- fused exchange -- into every peer's gather buffer.
+template <typename T>
+__device__ __forceinline__ void store_out(const DecodeParams& p, int64_t elem_off, const T& val) {
+  if (p.n_peers == 0) {
+    *reinterpret_cast<T*>(p.out + elem_off) = val;
+  } else {
+#pragma unroll 1
+    for (int r = 0; r < p.n_peers; ++r) *reinterpret_cast<T*>(p.peer_out[r] + elem_off) = val;
+  }
+}
+// Called by every warp that takes part in the output phase, after its stores: system-scope release, count, and
+// the last one publishes "this rank's heads are in your buffer" to every peer.
+__device__ __forceinline__ void signal_peers(const DecodeParams& p, int lane) {
+  if (p.n_peers == 0) return;
+  __threadfence_system();
+  __syncwarp();
+  if (lane == 0) {
+    const unsigned prev = atomicAdd(p.done, 1u);
+    if (prev == p.done_target - 1) {
+      atomicExch(p.done, 0u);
+      if (p.wait_n > 0) atomicAdd(p.wait_expected, 1u);   // every CTA has long read it: arm the next launch's wait
+      __threadfence_system();
+#pragma unroll 1
+      for (int r = 0; r < p.n_peers; ++r) atomicAdd_system(p.peer_flag[r], 1u);
+    }
+  }
 }
 
 template <int N>
@@ -185,7 +225,8 @@ __global__ void __launch_bounds__(kThreads, kPasses == 2 ? 2 : 1) decode_attn_ke
     *reinterpret_cast<Vec*>(&qcs) = __ldg(reinterpret_cast<const Vec*>(p.rope + pos * D + c * E2));
     *reinterpret_cast<Vec*>(&qsn) = __ldg(reinterpret_cast<const Vec*>(p.rope + pos * D + D / 2 + c * E2));
   };
-  if (p.pdl != 2) load_query();
+  const bool late_query = p.pdl == 2 || p.wait_n > 0;
+  if (!late_query) load_query();
   HV cs[kPasses], sn[kPasses];
   if (nt > 0) load_table(t0, cs, sn);
 
@@ -210,9 +251,22 @@ __global__ void __launch_bounds__(kThreads, kPasses == 2 ? 2 : 1) decode_attn_ke
     for (int i = 0; i < min(nt, kStages); ++i) issue(i);
   }
   __syncwarp();
-  if (p.pdl == 2) {
+  if (late_query) {
     // K/V prefetch overlapped the previous kernel; everything it may have produced is read after this
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (p.pdl == 2) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (p.wait_n > 0) {
+      // fused exchange, consumer side: the query depends on every rank's heads of the previous layer
+      const unsigned want = *reinterpret_cast<volatile const unsigned*>(p.wait_expected) + 1;
+      if (lane < p.wait_n) {
+        const long long tw = clock64();
+        unsigned v;
+        do {
+          asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.wait_flags + lane) : "memory");
+          if (clock64() - tw > 4000000000ll) { atomicExch(p.wait_timeout, 1u); break; }
+        } while (static_cast<int>(v - want) < 0);
+      }
+      __syncwarp();
+    }
     load_query();
   }
 
@@ -457,7 +511,7 @@ __global__ void __launch_bounds__(kThreads, kPasses == 2 ? 2 : 1) decode_attn_ke
           if (lane < 4 && d0 + lane < DW) {
             const float mine = lane == 0 ? o[0] : (lane == 1 ? o[1] : (lane == 2 ? o[2] : o[3]));
             const __half o16 = __float2half_rn(mine * inv);
-            p.out[static_cast<int64_t>(mrow) * D + slice * DS + warp * DW + d0 + lane] = o16;
+            store_out(p, static_cast<int64_t>(mrow) * D + slice * DS + warp * DW + d0 + lane, o16);
             habs += fabsf(__half2float(o16));
           }
         }
@@ -481,6 +535,7 @@ __global__ void __launch_bounds__(kThreads, kPasses == 2 ? 2 : 1) decode_attn_ke
       }
     }
     STAMP(6);
+    signal_peers(p, lane);                               // every warp of every CTA reaches this point
     return;
   } else {
     if (p.n_splits == 1) {
@@ -497,9 +552,8 @@ __global__ void __launch_bounds__(kThreads, kPasses == 2 ? 2 : 1) decode_attn_ke
             const float2 a = __half22float2(ol.h[i]), b = __half22float2(oh.h[i]);
             habs += fabsf(a.x) + fabsf(a.y) + fabsf(b.x) + fabsf(b.y);
           }
-          __half* o = p.out + static_cast<int64_t>(row) * D;
-          *reinterpret_cast<Vec*>(o + c * E2) = *reinterpret_cast<Vec*>(&ol);
-          *reinterpret_cast<Vec*>(o + D / 2 + c * E2) = *reinterpret_cast<Vec*>(&oh);
+          store_out(p, static_cast<int64_t>(row) * D + c * E2, *reinterpret_cast<Vec*>(&ol));
+          store_out(p, static_cast<int64_t>(row) * D + D / 2 + c * E2, *reinterpret_cast<Vec*>(&oh));
         }
         if (p.head_importance) {
           habs = warp_sum(habs);
@@ -515,6 +569,7 @@ __global__ void __launch_bounds__(kThreads, kPasses == 2 ? 2 : 1) decode_attn_ke
             imp[j] += fast_exp2((__half2float(s16) - m) * kLog2e) * inv;
           }
         }
+        signal_peers(p, lane);                           // one count per row
       }
       return;
     }
@@ -603,9 +658,8 @@ __global__ void __launch_bounds__(kThreads, kPasses == 2 ? 2 : 1) decode_attn_ke
       oh16[i] = __float2half_rn(o[i] * inv);
       habs += fabsf(__half2float(oh16[i]));
     }
-    __half* od = p.out + static_cast<int64_t>(row) * D + lane * PER;
-    if (PER == 4) *reinterpret_cast<uint2*>(od) = *reinterpret_cast<uint2*>(oh16);
-    else *reinterpret_cast<uint32_t*>(od) = *reinterpret_cast<uint32_t*>(oh16);
+    if (PER == 4) store_out(p, static_cast<int64_t>(row) * D + lane * PER, *reinterpret_cast<uint2*>(oh16));
+    else store_out(p, static_cast<int64_t>(row) * D + lane * PER, *reinterpret_cast<uint32_t*>(oh16));
     if (p.head_importance) {
       habs = warp_sum(habs);
       if (lane == 0) atomicAdd(p.head_importance + h, habs);
@@ -621,6 +675,7 @@ __global__ void __launch_bounds__(kThreads, kPasses == 2 ? 2 : 1) decode_attn_ke
     }
     STAMP(6);   // merged
     if (lane == 0) p.counters[row] = 0;         // self-cleaning ticket for the next launch
+    signal_peers(p, lane);                      // one count per row
   }
 #undef STAMP
 }
@@ -782,7 +837,7 @@ extern "C" int spatten_decode_attn(const SpattenDecodeArgs* a, void* stream) {
   SPATTEN_CHECK_ARG(n_total > 0, "spatten_decode_attn: nothing to attend over (kv_len 0 and append 0)");
   SPATTEN_CHECK_ARG(a->rope_len >= n_total, "spatten_decode_attn: rope_len %d < kv_len+append %d", a->rope_len, n_total);
   SPATTEN_CHECK_ARG(a->q && a->k_cache && a->v_cache && a->rope, "spatten_decode_attn: NULL q/k_cache/v_cache/rope");
-  SPATTEN_CHECK_ARG(a->out || (a->flags & SPATTEN_DECODE_SCORES_ONLY), "spatten_decode_attn: NULL out");
+  SPATTEN_CHECK_ARG(a->out || a->n_peers > 0 || (a->flags & SPATTEN_DECODE_SCORES_ONLY), "spatten_decode_attn: NULL out");
   SPATTEN_CHECK_ARG(!a->append || (a->k_new && a->v_new), "spatten_decode_attn: append=1 needs k_new and v_new");
   SPATTEN_CHECK_ARG(a->cache_stride_h >= static_cast<int64_t>(n_total) * a->head_dim,
                     "spatten_decode_attn: cache_stride_h %lld too small for %d tokens", (long long)a->cache_stride_h, n_total);
@@ -790,7 +845,7 @@ extern "C" int spatten_decode_attn(const SpattenDecodeArgs* a, void* stream) {
                     "spatten_decode_attn: cache_stride_b too small");
   SPATTEN_CHECK_ARG(a->cache_stride_h % 8 == 0 && a->cache_stride_b % 8 == 0,
                     "spatten_decode_attn: cache strides must be multiples of 8 elements (16-byte rows)");
-  const uintptr_t al = reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k_cache) |
+  uintptr_t al = reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k_cache) |
                        reinterpret_cast<uintptr_t>(a->v_cache) | reinterpret_cast<uintptr_t>(a->rope) |
                        reinterpret_cast<uintptr_t>(a->out) | reinterpret_cast<uintptr_t>(a->k_new) |
                        reinterpret_cast<uintptr_t>(a->v_new);
@@ -870,6 +925,27 @@ extern "C" int spatten_decode_attn(const SpattenDecodeArgs* a, void* stream) {
   // The small-footprint build is opt-in: measured on B200 (profiles/r1_microbench_decode_v11.jsonl) two co-resident
   // CTAs of consecutive PDL launches compete more than they overlap (config 2: 14.5 us vs 10.5 us per layer).
   p.passes = (a->flags & SPATTEN_DECODE_SMALL_TILES) ? 2 : 4;
+  p.n_peers = 0;
+  if (a->n_peers > 0 && !p.scores_only) {
+    SPATTEN_CHECK_ARG(a->n_peers <= kMaxPeers && a->done_counter != nullptr, "spatten_decode_attn: bad n_peers / done_counter");
+    for (int r = 0; r < a->n_peers; ++r) {
+      SPATTEN_CHECK_ARG(a->peer_out[r] && a->peer_flags[r], "spatten_decode_attn: NULL peer_out / peer_flags entry");
+      p.peer_out[r] = static_cast<__half*>(a->peer_out[r]);
+      p.peer_flag[r] = static_cast<unsigned int*>(a->peer_flags[r]);
+    }
+    p.n_peers = a->n_peers;
+    p.done = static_cast<unsigned int*>(a->done_counter);
+    p.done_target = p.cluster ? static_cast<unsigned>(p.n_rg) * p.cluster * kWarps : static_cast<unsigned>(p.rows);
+    p.wait_n = 0;
+    if (a->wait_n > 0) {
+      SPATTEN_CHECK_ARG(a->wait_n <= 32 && a->wait_flags && a->wait_expected && a->wait_timeout,
+                        "spatten_decode_attn: wait_n needs wait_flags, wait_expected and wait_timeout");
+      p.wait_flags = static_cast<const unsigned int*>(a->wait_flags);
+      p.wait_expected = static_cast<unsigned int*>(a->wait_expected);
+      p.wait_timeout = static_cast<unsigned int*>(a->wait_timeout);
+      p.wait_n = a->wait_n;
+    }
+  }
   if (p.n_splits > 1 && !p.cluster) {
     const size_t need = spatten_decode_workspace_bytes(a->batch, a->num_heads, a->head_dim);
     if (a->workspace == nullptr || a->workspace_bytes < need) {
@@ -909,4 +985,33 @@ extern "C" int spatten_decode_attn_host(const SpattenDecodeArgs* a, const void* 
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return cuda_fail(e, "spatten_decode_attn_host: D2H copy / sync");
   return SPATTEN_OK;
+}
+
+// ---- consumer side of the fused exchange ------------------------------------------------------------------------
+namespace spatten {
+__global__ void wait_flags_kernel(const unsigned int* flags, int n, unsigned int* expected, unsigned int* timed_out) {
+  __shared__ unsigned int s_exp;
+  if (threadIdx.x == 0) s_exp = *expected + 1;
+  __syncthreads();
+  const unsigned int want = s_exp;
+  if (threadIdx.x < n) {
+    const long long t0 = clock64();
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+      if (clock64() - t0 > 4000000000ll) { atomicExch(timed_out, 1u); break; }   // ~2 s: never wedge the GPU
+    } while (static_cast<int>(v - want) < 0);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *expected = want;
+}
+}  // namespace spatten
+
+extern "C" int spatten_wait_flags(const void* flags, int32_t n, void* expected_counter, void* timeout_flag, void* stream) {
+  SPATTEN_CHECK_ARG(flags && expected_counter && timeout_flag && n > 0 && n <= 32, "spatten_wait_flags: bad arguments");
+  spatten::wait_flags_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const unsigned int*>(flags), n, static_cast<unsigned int*>(expected_counter),
+      static_cast<unsigned int*>(timeout_flag));
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? SPATTEN_OK : spatten::cuda_fail(e, "wait_flags_kernel launch");
 }

@@ -65,3 +65,62 @@ def gathered_to_heads(slots: torch.Tensor) -> torch.Tensor:
     """[N, b, H/N, D] -> [b, H, D] with heads in global order (rank-major head blocks)."""
     n, b, hl, d = slots.shape
     return slots.permute(1, 0, 2, 3).reshape(b, n * hl, d)
+
+
+class PeerExchange:
+    """Fused output exchange over NVLink peer memory (no collective kernel).
+
+    One symmetric allocation per rank holds the gather buffers of all layers, fp16 [L, N, b, H/N, D], and one
+    flag word per (layer, producing rank).  `spatten_decode_attn` stores its output rows straight into slot
+    `rank` of every peer's buffer and, when its whole grid is done, bumps flag [layer, rank] on every peer;
+    `wait(layer)` (spatten_wait_flags) blocks the stream until all N producers have reported for this step.
+    Memory is mapped with torch.distributed._symmetric_memory (CUDA VMM / fabric handles under the hood).
+    """
+
+    def __init__(self, layers: int, shard: HeadShard, batch: int, head_dim: int, device, group=None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self._C, self._lib = C, _lib
+        self.shard, self.layers = shard, layers
+        n, hl = shard.world, shard.count
+        self.slot_elems = batch * hl * head_dim
+        out_bytes = layers * n * self.slot_elems * 2
+        self.flag_off = (out_bytes + 255) // 256 * 256
+        total = self.flag_off + layers * n * 4
+        self.buf = symm.empty(total, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        group = group if group is not None else dist.group.WORLD
+        self.hdl = symm.rendezvous(self.buf, group)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.gathered = self.buf[:out_bytes].view(torch.float16).view(layers, n, batch, hl, head_dim)
+        self.flags = self.buf[self.flag_off:self.flag_off + layers * n * 4].view(torch.int32).view(layers, n)
+        self.done = torch.zeros(layers, dtype=torch.int32, device=device)
+        self.expected = torch.zeros(layers, dtype=torch.int32, device=device)
+        self.timeout = torch.zeros(1, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)
+
+    def fill_args(self, a, layer: int, wait_on_layer=None) -> None:
+        """Point a SpattenDecodeArgs at the peers' slots for `layer`; with `wait_on_layer` the kernel itself waits
+        for that (earlier) layer's exchange before it reads its query, so no wait launch is needed in between."""
+        n, r = self.shard.world, self.shard.rank
+        if wait_on_layer is not None:
+            a.wait_n = n
+            a.wait_flags = self.flags[wait_on_layer].data_ptr()
+            a.wait_expected = self.expected[wait_on_layer:].data_ptr()
+            a.wait_timeout = self.timeout.data_ptr()
+        a.n_peers = n
+        for p in range(n):
+            a.peer_out[p] = self.ptrs[p] + ((layer * n + r) * self.slot_elems) * 2
+            a.peer_flags[p] = self.ptrs[p] + self.flag_off + (layer * n + r) * 4
+        a.done_counter = self.done[layer:].data_ptr()
+
+    def wait(self, layer: int, stream_ptr: int) -> None:
+        lib = self._lib.load()
+        self._lib.check(lib.spatten_wait_flags(self.flags[layer].data_ptr(), self.shard.world,
+                                               self.expected[layer:].data_ptr(), self.timeout.data_ptr(),
+                                               self._C.c_void_p(stream_ptr)))
+
+    def timed_out(self) -> bool:
+        return bool(self.timeout.item())
