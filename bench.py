@@ -231,8 +231,11 @@ def run_ours(args):
             layer_args.append(a)
             keep.append(ka)
 
-    def attn_layer(l):
-        _lib.check(lib.spatten_decode_attn(C.byref(layer_args[l]), sptr))
+    # the same launches without any exchange (local `out` only): the kernel-only region of the roofline at N > 1
+    local_args = [_lib.DecodeArgs.from_buffer_copy(a) for a in layer_args]
+
+    def attn_layer(l, exchange=True):
+        _lib.check(lib.spatten_decode_attn(C.byref(layer_args[l] if exchange else local_args[l]), sptr))
 
     from spatten_b200.parallel import HeadShard, PeerExchange, exchange_heads
     shard = HeadShard(rank, world, H)
@@ -254,14 +257,10 @@ def run_ours(args):
         # zero-padded all-reduce (re-zeroes the peers' slots first) or all-gather of the per-rank head blocks
         exchange_heads(gathered[l], shard, args.collective)
 
-    def rezero(l):
-        pass
 
     def step_eager(with_collective=True):
         for l in range(L):
-            if with_collective:
-                rezero(l)
-            attn_layer(l)
+            attn_layer(l, with_collective)
             if with_collective:
                 collective(l)
 
@@ -362,6 +361,7 @@ def run_ours(args):
     for l in range(L):
         a = _lib.DecodeArgs.from_buffer_copy(layer_args[l])
         a.flags = 0
+        a.wait_n = 0                                # e2e waits for every layer's exchange explicitly (output goes to the host)
         e2e_args.append(a)
 
     def e2e_step():
@@ -374,9 +374,11 @@ def run_ours(args):
                     q[l].copy_(hq[l], non_blocking=True)
                     kn[l].copy_(hk[l], non_blocking=True)
                     vn[l].copy_(hv[l], non_blocking=True)
-                    rezero(l)
                     _lib.check(lib.spatten_decode_attn(C.byref(e2e_args[l]), sptr))
-                    collective(l)
+                    if px is not None:
+                        px.wait(l, stream.cuda_stream)
+                    else:
+                        collective(l)
                     hout[l].copy_(gathered[l], non_blocking=True)
                     stream.synchronize()
 

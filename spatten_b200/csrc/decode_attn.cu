@@ -114,13 +114,20 @@ __device__ __forceinline__ void store_out(const DecodeParams& p, int64_t elem_of
     for (int r = 0; r < p.n_peers; ++r) *reinterpret_cast<T*>(p.peer_out[r] + elem_off) = val;
   }
 }
-// Called by every warp that takes part in the output phase, after its stores: system-scope release, count, and
-// the last one publishes "this rank's heads are in your buffer" to every peer.
+// Called after the output stores by every participant (a warp; in cluster mode, where all warps of all CTAs take
+// part, a whole CTA): system-scope release, count, and the last one publishes "this rank's heads are in your
+// buffer" to every peer.
+template <bool kWholeCta>
 __device__ __forceinline__ void signal_peers(const DecodeParams& p, int lane) {
   if (p.n_peers == 0) return;
-  __threadfence_system();
-  __syncwarp();
+  if (kWholeCta) {
+    __syncthreads();                       // the CTA's stores are ordered before thread 0's fence (cumulativity)
+    if (threadIdx.x != 0) return;
+  } else {
+    __syncwarp();
+  }
   if (lane == 0) {
+    __threadfence_system();
     const unsigned prev = atomicAdd(p.done, 1u);
     if (prev == p.done_target - 1) {
       atomicExch(p.done, 0u);
@@ -535,7 +542,7 @@ __global__ void __launch_bounds__(kThreads, kPasses == 2 ? 2 : 1) decode_attn_ke
       }
     }
     STAMP(6);
-    signal_peers(p, lane);                               // every warp of every CTA reaches this point
+    signal_peers<true>(p, lane);                         // every warp of every CTA reaches this point
     return;
   } else {
     if (p.n_splits == 1) {
@@ -569,7 +576,7 @@ __global__ void __launch_bounds__(kThreads, kPasses == 2 ? 2 : 1) decode_attn_ke
             imp[j] += fast_exp2((__half2float(s16) - m) * kLog2e) * inv;
           }
         }
-        signal_peers(p, lane);                           // one count per row
+        signal_peers<false>(p, lane);                    // one count per row
       }
       return;
     }
@@ -675,7 +682,7 @@ __global__ void __launch_bounds__(kThreads, kPasses == 2 ? 2 : 1) decode_attn_ke
     }
     STAMP(6);   // merged
     if (lane == 0) p.counters[row] = 0;         // self-cleaning ticket for the next launch
-    signal_peers(p, lane);                      // one count per row
+    signal_peers<false>(p, lane);               // one count per row
   }
 #undef STAMP
 }
@@ -935,7 +942,7 @@ extern "C" int spatten_decode_attn(const SpattenDecodeArgs* a, void* stream) {
     }
     p.n_peers = a->n_peers;
     p.done = static_cast<unsigned int*>(a->done_counter);
-    p.done_target = p.cluster ? static_cast<unsigned>(p.n_rg) * p.cluster * kWarps : static_cast<unsigned>(p.rows);
+    p.done_target = p.cluster ? static_cast<unsigned>(p.n_rg) * p.cluster : static_cast<unsigned>(p.rows);
     p.wait_n = 0;
     if (a->wait_n > 0) {
       SPATTEN_CHECK_ARG(a->wait_n <= 32 && a->wait_flags && a->wait_expected && a->wait_timeout,
