@@ -152,6 +152,31 @@ int spatten_decode_attn_host(const SpattenDecodeArgs* args, const void* q_host, 
                              const void* v_new_host, void* out_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Prefill attention (q_len > 1) on the tcgen05 tensor cores.  Same reference lines as spatten_decode_attn
+ * (modify_llama.py:86-144) in the reference's own three steps, because the full pre-mask logit matrix is an
+ * output (`self.attn_scores`, :116-119): S = rope(Q).rope(K)^T (UMMA, RoPE fused into the operand staging,
+ * fp16 logit formed as :111-113), P = softmax(S + mask) in fp32 (:132-137), O = P.V (UMMA).
+ * The new K/V rows must already be in the cache (rows [kv_len - q_len, kv_len) for a plain prefill).
+ * head_dim == 128.  `probs` is scratch of the same shape and strides as `logits`.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct SpattenPrefillArgs {
+  uint32_t struct_size;
+  int32_t batch, num_heads, num_kv_heads, head_dim, q_len, kv_len, rope_len;
+  const void* q;            /* fp16 [b, q_len, H, D] un-rotated */
+  const void* k_cache;      /* fp16 [b, H_kv, >= kv_len, D] un-rotated */
+  const void* v_cache;
+  int64_t cache_stride_b, cache_stride_h;   /* elements */
+  const void* rope;         /* fp16 [rope_len, D] */
+  const int64_t* q_pos;     /* [b, q_len] */
+  const void* mask;         /* optional fp16 additive [b, q_len, kv_len] */
+  void* logits;             /* out fp16 attn_scores[b, h, q, :] */
+  int64_t logits_stride_b, logits_stride_h, logits_stride_q;   /* elements */
+  void* probs;              /* scratch fp16, same strides */
+  void* out;                /* fp16 [b, q_len, H, D] */
+} SpattenPrefillArgs;
+int spatten_prefill_attn(const SpattenPrefillArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * KV-cache token pruning.  Replaces SpAttenKVCache.apply_token_pruning
  * (spatten_llm/kv_cache_token_pruning.py:42-96) with three device-side steps and no host sync
  * (the reference synchronises once per layer through `.cpu()`, :66).

@@ -48,6 +48,19 @@ class DecodeArgs(C.Structure):
     ]
 
 
+class PrefillArgs(C.Structure):
+    """Mirror of `SpattenPrefillArgs`."""
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("batch", C.c_int32), ("num_heads", C.c_int32), ("num_kv_heads", C.c_int32),
+        ("head_dim", C.c_int32), ("q_len", C.c_int32), ("kv_len", C.c_int32), ("rope_len", C.c_int32),
+        ("q", C.c_void_p), ("k_cache", C.c_void_p), ("v_cache", C.c_void_p),
+        ("cache_stride_b", C.c_int64), ("cache_stride_h", C.c_int64),
+        ("rope", C.c_void_p), ("q_pos", C.c_void_p), ("mask", C.c_void_p),
+        ("logits", C.c_void_p), ("logits_stride_b", C.c_int64), ("logits_stride_h", C.c_int64),
+        ("logits_stride_q", C.c_int64), ("probs", C.c_void_p), ("out", C.c_void_p),
+    ]
+
+
 class SelectArgs(C.Structure):
     """Mirror of `SpattenSelectArgs`."""
     _fields_ = [
@@ -143,6 +156,7 @@ def _bind_optional(lib):
     lib.spatten_topk_select.argtypes = [C.POINTER(SelectArgs), C.c_void_p]
     lib.spatten_kv_gather.argtypes = [C.POINTER(GatherArgs), C.c_void_p]
     lib.spatten_sparse_pv.argtypes = [C.POINTER(SparsePvArgs), C.c_void_p]
+    lib.spatten_prefill_attn.argtypes = [C.POINTER(PrefillArgs), C.c_void_p]
     lib.spatten_wait_flags.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.spatten_kv_quantize.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                         C.c_int32, C.c_int32, C.POINTER(QuantKV), C.c_int32, C.c_void_p]

@@ -917,6 +917,7 @@ extern "C" int spatten_decode_attn(const SpattenDecodeArgs* a, void* stream) {
         const int n_cl = (p.rows + rpc - 1) / rpc;
         const int spc = kWarps / rpc;
         const int ctas = n_cl * cs;
+        if (rpc > cs) continue;                          // every row is finished by cs / rpc >= 1 CTAs of its cluster
         if (n_cl > max_cl || ctas > sms || ctas * 4 < sms * 3 || ctas <= best_ctas) continue;
         if (a->kv_len < cs * spc * 16) continue;
         best_ctas = ctas;

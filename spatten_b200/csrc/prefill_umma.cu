@@ -1,0 +1,394 @@
+// Prefill attention on the 5th-generation tensor cores -- spatten_prefill_attn().
+//
+// Replaces llama_pos_shift_attention_forward for q_len > 1 (reference spatten_llm/pos_shift/modify_llama.py:86-144)
+// with the reference's own three-step structure, because the reference *exports* the full pre-mask logit matrix
+// (`self.attn_scores`, :116-119) and masks additively (:127-132), so S = Q.K^T has to be materialised anyway:
+//   1. umma_qk_kernel   S[q, kv] = rope(Q) . rope(K)^T          tcgen05.mma (UMMA) 128x128 tiles, fp32 in TMEM; RoPE is
+//                                                               applied by the producer threads on the way into shared
+//                                                               memory (fp16, op for op, :27); epilogue writes the fp16
+//                                                               logit exactly as the reference forms it (:111-113)
+//   2. softmax_rows_kernel  P = softmax(S + mask) in fp32 -> fp16 (:132-137)
+//   3. umma_pv_kernel   O[q, D] = P . V                          tcgen05.mma with an MN-major B operand (V rows as stored)
+// Operands are staged in the canonical no-swizzle UMMA layout (8x8-element core matrices of 128 contiguous bytes;
+// K-major: LBO = 128 B between K chunks, SBO between 8-row groups) by plain 128-bit loads/stores: the tiles are
+// rotated (Q, K) or used once (P, V), so there is no TMA tensor map.  One elected thread issues the MMAs and
+// tcgen05.commit signals an mbarrier; four warps read the accumulator back with tcgen05.ld (32 lanes each).
+#include <math_constants.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "../../include/spatten_b200.h"
+#include "common.cuh"
+
+namespace spatten {
+
+constexpr int kUThreads = 128;     // 4 warps: producers, then epilogue (warp w owns TMEM lanes 32w..32w+31)
+constexpr int kTileM = 128;
+constexpr int kTileN = 128;
+
+// ---- tcgen05 wrappers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48)
+  // | layout_type [61,64) = 0 (SWIZZLE_NONE / interleave)
+  return static_cast<uint64_t>((saddr >> 4) & 0x3FFFu) | (static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         (static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// InstrDescriptor for kind::f16: D = f32, A = B = f16, A K-major, B K-major (0) or MN-major (1), N, M
+__host__ __device__ constexpr uint32_t umma_idesc(int m, int n, int b_mn_major) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(b_mn_major) << 16) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(static_cast<uint32_t>(accumulate))
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// mbarrier wait that cannot wedge the GPU: a tensor-core commit that never arrives (a malformed descriptor) traps
+// after ~1 s instead of spinning forever
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 2000000000ll) __trap();
+  }
+}
+
+// byte offset of the 16-byte piece (row r, 8-element K chunk c) inside a K-major no-swizzle tile with `chunks`
+// K chunks per row: core matrix (r/8, c) at (r/8)*chunks*128 + c*128, row r%8 inside it
+__device__ __forceinline__ uint32_t kmajor_off(int r, int c, int chunks) {
+  return static_cast<uint32_t>((r >> 3) * chunks * 128 + c * 128 + (r & 7) * 16);
+}
+
+__device__ __forceinline__ float pf_div_by_const(float x, float c, float rc) {
+  const float y = x * rc;
+  const float r = fmaf(-y, c, x);
+  const float y2 = fmaf(r, rc, y);
+  return (fabsf(y2) <= 3.4028234e38f) ? y2 : y;
+}
+
+struct PrefillParams {
+  const __half* q;          // [b, q_len, H, D] un-rotated
+  const __half* k_cache;    // [b, H_kv, >=kv_len, D] un-rotated (new rows already stored)
+  const __half* v_cache;
+  int64_t stride_b, stride_h;
+  const __half* rope;       // [rope_len, D]: cos | sin first halves
+  const int64_t* q_pos;     // [b, q_len]
+  const __half* mask;       // optional [b, q_len, kv_len]
+  __half* logits;           // [b, H, q_len, kv_len] strides below
+  int64_t ls_b, ls_h, ls_q;
+  __half* probs;            // scratch, same shape/strides as logits
+  __half* out;              // [b, q_len, H, D]
+  int batch, H, n_rep, q_len, kv_len, rope_len;
+  float sqrt_d, rsqrt_d;
+};
+
+// ---- 1. S = rope(Q) . rope(K)^T -----------------------------------------------------------------------------------
+// grid (ceil(kv/128), ceil(q/128), b*H); 128 threads.  Whole head_dim in one K block (D/16 MMAs of K = 16).
+template <int D>
+__global__ void __launch_bounds__(kUThreads) umma_qk_kernel(const PrefillParams p) {
+  constexpr int kChunks = D / 8;                       // 16-byte K chunks per row
+  constexpr int kTileBytes = kTileM * D * 2;           // 32 KiB (D = 128)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kTileBytes;
+  __shared__ uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bh = blockIdx.z, b = bh / p.H, h = bh % p.H, kvh = h / p.n_rep;
+  const int m0 = blockIdx.y * kTileM, n0 = blockIdx.x * kTileN;
+
+  if (warp == 0) tmem_alloc(&s_tmem, kTileN);
+  if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
+
+  // producers: rows of Q (rotated at q_pos) and of K (rotated at the slot index), fp16 op for op (:21-28)
+  const __half* Kc = p.k_cache + b * p.stride_b + kvh * p.stride_h;
+  for (int piece = tid; piece < kTileM * (kChunks / 2); piece += kUThreads) {
+    const int r = piece / (kChunks / 2), c = piece % (kChunks / 2);      // row, chunk of the FIRST half; partner c + kChunks/2
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const int row = (which ? n0 : m0) + r;
+      const bool ok = row < (which ? p.kv_len : p.q_len);
+      uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+      if (ok) {
+        const __half* src = which ? Kc + static_cast<int64_t>(row) * D
+                                  : p.q + ((static_cast<int64_t>(b) * p.q_len + row) * p.H + h) * D;
+        int64_t pos = which ? row : p.q_pos[static_cast<int64_t>(b) * p.q_len + row];
+        pos = max(static_cast<int64_t>(0), min(pos, static_cast<int64_t>(p.rope_len - 1)));
+        const uint4 xl = *reinterpret_cast<const uint4*>(src + c * 8);
+        const uint4 xh = *reinterpret_cast<const uint4*>(src + D / 2 + c * 8);
+        const uint4 cs = __ldg(reinterpret_cast<const uint4*>(p.rope + pos * D + c * 8));
+        const uint4 sn = __ldg(reinterpret_cast<const uint4*>(p.rope + pos * D + D / 2 + c * 8));
+        const __half2* a = reinterpret_cast<const __half2*>(&xl);
+        const __half2* bb = reinterpret_cast<const __half2*>(&xh);
+        const __half2* c2 = reinterpret_cast<const __half2*>(&cs);
+        const __half2* s2 = reinterpret_cast<const __half2*>(&sn);
+        __half2* ol = reinterpret_cast<__half2*>(&lo);
+        __half2* oh = reinterpret_cast<__half2*>(&hi);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          ol[i] = __hsub2_rn(__hmul2_rn(a[i], c2[i]), __hmul2_rn(bb[i], s2[i]));
+          oh[i] = __hadd2_rn(__hmul2_rn(bb[i], c2[i]), __hmul2_rn(a[i], s2[i]));
+        }
+      }
+      uint8_t* dst = which ? sB : sA;
+      *reinterpret_cast<uint4*>(dst + kmajor_off(r, c, kChunks)) = lo;
+      *reinterpret_cast<uint4*>(dst + kmajor_off(r, c + kChunks / 2, kChunks)) = hi;
+    }
+  }
+  fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  if (tid == 0) {
+    constexpr uint32_t idesc = umma_idesc(kTileM, kTileN, 0);
+#pragma unroll
+    for (int ks = 0; ks < D / 16; ++ks) {
+      const uint64_t ad = umma_desc(smem_u32(sA) + ks * 256, 128, kChunks * 128);
+      const uint64_t bd = umma_desc(smem_u32(sB) + ks * 256, 128, kChunks * 128);
+      umma_f16(tmem, ad, bd, idesc, ks > 0);
+    }
+    umma_commit(&s_bar);
+  }
+  mbar_wait_bounded(&s_bar, 0);
+  tc_fence_after();
+
+  // epilogue: warp w owns rows 32w..32w+31 (TMEM lanes); fp16(acc) / sqrt(D) -> fp16 (:111-113)
+  const int row = m0 + warp * 32 + lane;
+  __half* dst = p.logits + b * p.ls_b + h * p.ls_h + static_cast<int64_t>(row) * p.ls_q + n0;
+#pragma unroll 1
+  for (int cb = 0; cb < kTileN; cb += 32) {
+    float v[32];
+    tmem_ld32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + cb, v);
+    if (row < p.q_len) {
+      __align__(16) __half o[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        o[i] = __float2half_rn(pf_div_by_const(__half2float(__float2half_rn(v[i])), p.sqrt_d, p.rsqrt_d));
+      if (n0 + cb + 32 <= p.kv_len && ((reinterpret_cast<uintptr_t>(dst + cb) & 15) == 0)) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(dst + cb)[i] = reinterpret_cast<const uint4*>(o)[i];
+      } else {
+        for (int i = 0; i < 32; ++i)
+          if (n0 + cb + i < p.kv_len) dst[cb + i] = o[i];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, kTileN);
+}
+
+// ---- 2. P = softmax(S + mask), fp32 (:132-137) ---------------------------------------------------------------------
+// one warp per (b, h, q) row
+__global__ void softmax_rows_kernel(const PrefillParams p) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int64_t rows = static_cast<int64_t>(p.batch) * p.H * p.q_len;
+  if (row >= rows) return;
+  const int qi = row % p.q_len, h = (row / p.q_len) % p.H, b = row / (static_cast<int64_t>(p.q_len) * p.H);
+  const __half* s = p.logits + b * p.ls_b + h * p.ls_h + static_cast<int64_t>(qi) * p.ls_q;
+  __half* o = p.probs + b * p.ls_b + h * p.ls_h + static_cast<int64_t>(qi) * p.ls_q;
+  const __half* mk = p.mask ? p.mask + (static_cast<int64_t>(b) * p.q_len + qi) * p.kv_len : nullptr;
+  float mx = -CUDART_INF_F;
+  for (int j = lane; j < p.kv_len; j += 32) {
+    __half x = s[j];
+    if (mk) x = __hadd_rn(x, mk[j]);
+    mx = fmaxf(mx, __half2float(x));
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < p.kv_len; j += 32) {
+    __half x = s[j];
+    if (mk) x = __hadd_rn(x, mk[j]);
+    sum += __expf(__half2float(x) - mx);
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  for (int j = lane; j < p.kv_len; j += 32) {
+    __half x = s[j];
+    if (mk) x = __hadd_rn(x, mk[j]);
+    o[j] = __float2half_rn(__expf(__half2float(x) - mx) * inv);
+  }
+}
+
+// ---- 3. O = P . V --------------------------------------------------------------------------------------------------
+// grid (1, ceil(q/128), b*H); N = D; K loop over kv in blocks of 64.  A = P rows (K-major), B = V rows as stored
+// (MN-major: 16 bytes along D, 8 tokens per core matrix).
+template <int D>
+__global__ void __launch_bounds__(kUThreads) umma_pv_kernel(const PrefillParams p) {
+  constexpr int BK = 64;
+  constexpr int kAChunks = BK / 8;                      // 8 K chunks per P row
+  constexpr int kABytes = kTileM * BK * 2;              // 16 KiB
+  constexpr int kBBytes = BK * D * 2;                   // 16 KiB (D = 128)
+  constexpr int kNChunks = D / 8;                       // 16-byte chunks along D
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kABytes;
+  __shared__ uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bh = blockIdx.z, b = bh / p.H, h = bh % p.H, kvh = h / p.n_rep;
+  const int m0 = blockIdx.y * kTileM;
+  if (warp == 0) tmem_alloc(&s_tmem, D < 32 ? 32 : D);
+  if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  const __half* P = p.probs + b * p.ls_b + h * p.ls_h;
+  const __half* V = p.v_cache + b * p.stride_b + kvh * p.stride_h;
+  const bool vec_ok = (p.ls_q % 8) == 0 && ((reinterpret_cast<uintptr_t>(P) & 15) == 0);
+  uint32_t phase = 0;
+  const int nk = (p.kv_len + BK - 1) / BK;
+  for (int kb = 0; kb < nk; ++kb) {
+    const int k0 = kb * BK;
+    // A: P[m0 + r, k0 + 8c .. +8)
+    for (int piece = tid; piece < kTileM * kAChunks; piece += kUThreads) {
+      const int r = piece / kAChunks, c = piece % kAChunks;
+      uint4 val = make_uint4(0, 0, 0, 0);
+      const int row = m0 + r, col = k0 + c * 8;
+      if (row < p.q_len && col < p.kv_len) {
+        const __half* src = P + static_cast<int64_t>(row) * p.ls_q + col;
+        if (vec_ok && col + 8 <= p.kv_len) {
+          val = *reinterpret_cast<const uint4*>(src);
+        } else {
+          __align__(16) __half t[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[i] = (col + i < p.kv_len) ? src[i] : __float2half(0.f);
+          val = *reinterpret_cast<const uint4*>(t);
+        }
+      }
+      *reinterpret_cast<uint4*>(sA + kmajor_off(r, c, kAChunks)) = val;
+    }
+    // B: V[k0 + j, 8c .. +8): core matrix (token group j/8, D chunk c) at (j/8) * LBO + c * SBO, row j%8 inside
+    for (int piece = tid; piece < BK * kNChunks; piece += kUThreads) {
+      const int j = piece / kNChunks, c = piece % kNChunks;
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (k0 + j < p.kv_len) val = *reinterpret_cast<const uint4*>(V + static_cast<int64_t>(k0 + j) * D + c * 8);
+      *reinterpret_cast<uint4*>(sB + (j >> 3) * (kNChunks * 128) + c * 128 + (j & 7) * 16) = val;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+      constexpr uint32_t idesc = umma_idesc(kTileM, D, 1);
+#pragma unroll
+      for (int ks = 0; ks < BK / 16; ++ks) {
+        const uint64_t ad = umma_desc(smem_u32(sA) + ks * 256, 128, kAChunks * 128);
+        // MN-major B: 2 token groups per MMA; LBO = stride between token groups, SBO = stride between D chunks
+        const uint64_t bd = umma_desc(smem_u32(sB) + ks * 2 * (kNChunks * 128), kNChunks * 128, 128);
+        umma_f16(tmem, ad, bd, idesc, kb > 0 || ks > 0);
+      }
+      umma_commit(&s_bar);
+    }
+    mbar_wait_bounded(&s_bar, phase);           // the MMAs have consumed this block: shared memory may be overwritten
+    phase ^= 1;
+    tc_fence_after();
+  }
+
+  const int row = m0 + warp * 32 + lane;
+  __half* dst = p.out + ((static_cast<int64_t>(b) * p.q_len + row) * p.H + h) * D;
+#pragma unroll 1
+  for (int cb = 0; cb < D; cb += 32) {
+    float v[32];
+    tmem_ld32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + cb, v);
+    if (row < p.q_len) {
+      __align__(16) __half o[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = __float2half_rn(v[i]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(dst + cb)[i] = reinterpret_cast<const uint4*>(o)[i];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, D < 32 ? 32 : D);
+}
+
+}  // namespace spatten
+
+using namespace spatten;
+
+extern "C" int spatten_prefill_attn(const SpattenPrefillArgs* a, void* stream) {
+  SPATTEN_CHECK_ARG(a != nullptr && a->struct_size == sizeof(SpattenPrefillArgs), "spatten_prefill_attn: bad args/struct_size");
+  SPATTEN_CHECK_ARG(a->batch > 0 && a->num_heads > 0 && a->num_kv_heads > 0 && a->num_heads % a->num_kv_heads == 0,
+                    "spatten_prefill_attn: bad head counts");
+  if (a->head_dim != 128) { set_error("spatten_prefill_attn: head_dim %d unsupported (128)", a->head_dim); return SPATTEN_ERR_UNSUPPORTED; }
+  SPATTEN_CHECK_ARG(a->q_len > 0 && a->kv_len >= a->q_len && a->rope_len >= a->kv_len, "spatten_prefill_attn: bad q_len / kv_len / rope_len");
+  SPATTEN_CHECK_ARG(a->q && a->k_cache && a->v_cache && a->rope && a->q_pos && a->logits && a->probs && a->out,
+                    "spatten_prefill_attn: NULL pointer");
+  SPATTEN_CHECK_ARG(a->logits_stride_q >= a->kv_len, "spatten_prefill_attn: logits_stride_q < kv_len");
+  const uintptr_t al = reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k_cache) |
+                       reinterpret_cast<uintptr_t>(a->v_cache) | reinterpret_cast<uintptr_t>(a->rope) |
+                       reinterpret_cast<uintptr_t>(a->out);
+  SPATTEN_CHECK_ARG((al & 15) == 0 && a->cache_stride_b % 8 == 0 && a->cache_stride_h % 8 == 0,
+                    "spatten_prefill_attn: q/k_cache/v_cache/rope/out must be 16-byte aligned");
+  PrefillParams p{};
+  p.q = static_cast<const __half*>(a->q);
+  p.k_cache = static_cast<const __half*>(a->k_cache);
+  p.v_cache = static_cast<const __half*>(a->v_cache);
+  p.stride_b = a->cache_stride_b; p.stride_h = a->cache_stride_h;
+  p.rope = static_cast<const __half*>(a->rope); p.q_pos = a->q_pos; p.mask = static_cast<const __half*>(a->mask);
+  p.logits = static_cast<__half*>(a->logits); p.probs = static_cast<__half*>(a->probs); p.out = static_cast<__half*>(a->out);
+  p.ls_b = a->logits_stride_b; p.ls_h = a->logits_stride_h; p.ls_q = a->logits_stride_q;
+  p.batch = a->batch; p.H = a->num_heads; p.n_rep = a->num_heads / a->num_kv_heads; p.q_len = a->q_len; p.kv_len = a->kv_len; p.rope_len = a->rope_len;
+  p.sqrt_d = static_cast<float>(sqrt(static_cast<double>(a->head_dim))); p.rsqrt_d = 1.0f / p.sqrt_d;
+
+  constexpr int D = 128;
+  constexpr int smem_qk = 2 * kTileM * D * 2, smem_pv = kTileM * 64 * 2 + 64 * D * 2;
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !configured[dev]) {
+    cudaError_t e1 = cudaFuncSetAttribute(umma_qk_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_qk);
+    cudaError_t e2 = cudaFuncSetAttribute(umma_pv_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pv);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) return cuda_fail(e1 != cudaSuccess ? e1 : e2, "cudaFuncSetAttribute(umma kernels)");
+    configured[dev] = true;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int mt = (a->q_len + kTileM - 1) / kTileM, nt = (a->kv_len + kTileN - 1) / kTileN, bh = a->batch * a->num_heads;
+  umma_qk_kernel<D><<<dim3(nt, mt, bh), kUThreads, smem_qk, st>>>(p);
+  const int64_t rows = static_cast<int64_t>(a->batch) * a->num_heads * a->q_len;
+  softmax_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(p);
+  umma_pv_kernel<D><<<dim3(1, mt, bh), kUThreads, smem_pv, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? SPATTEN_OK : cuda_fail(e, "spatten_prefill_attn launch");
+}

@@ -135,6 +135,51 @@ def decode_attn(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, k
     return out
 
 
+def prefill_attn(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, kv_len: int, rope: torch.Tensor,
+                 q_pos: torch.Tensor, mask: Optional[torch.Tensor] = None, logits: Optional[torch.Tensor] = None):
+    """Prefill / chunk attention on the tcgen05 tensor cores -- `spatten_prefill_attn` (head_dim 128).
+
+    q fp16 [b,q_len,H,D] un-rotated; the new K/V rows are already in k_cache/v_cache [b,H_kv,cap,D]; kv_len rows
+    valid; q_pos int64 [b,q_len]; mask fp16 additive [b,q_len,kv_len].  Returns (out [b,q_len,H,D],
+    logits [b,H,q_len,kv_len] == attn_scores).
+    """
+    lib = _lib.load()
+    _require_cuda(q, k_cache, v_cache, rope, q_pos, mask, logits)
+    b, q_len, H, D = q.shape
+    H_kv = k_cache.shape[1]
+    if q.dtype != torch.float16 or k_cache.dtype != torch.float16 or v_cache.dtype != torch.float16:
+        raise TypeError("spatten_b200.prefill_attn: fp16 tensors required")
+    if k_cache.stride(3) != 1 or k_cache.stride(2) != D or v_cache.stride() != k_cache.stride():
+        raise ValueError("spatten_b200.prefill_attn: cache rows must be contiguous with equal K/V strides")
+    q = q.contiguous()
+    if logits is None:
+        logits = torch.empty((b, H, q_len, kv_len), dtype=torch.float16, device=q.device)
+    if logits.stride(3) != 1:
+        raise ValueError("logits last dimension must be contiguous")
+    probs = torch.empty_strided(logits.shape, logits.stride(), dtype=torch.float16, device=q.device)
+    out = torch.empty((b, q_len, H, D), dtype=torch.float16, device=q.device)
+    a = _lib.PrefillArgs()
+    a.struct_size = C.sizeof(_lib.PrefillArgs)
+    a.batch, a.num_heads, a.num_kv_heads, a.head_dim = b, H, H_kv, D
+    a.q_len, a.kv_len, a.rope_len = q_len, int(kv_len), rope.shape[0]
+    a.q, a.k_cache, a.v_cache = q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr()
+    a.cache_stride_b, a.cache_stride_h = k_cache.stride(0), k_cache.stride(1)
+    a.rope = rope.data_ptr()
+    if q_pos.dtype != torch.int64 or q_pos.numel() != b * q_len:
+        raise TypeError("q_pos must be int64 [b, q_len]")
+    q_pos = q_pos.contiguous()
+    a.q_pos = q_pos.data_ptr()
+    if mask is not None:
+        if mask.dtype != torch.float16 or mask.numel() != b * q_len * kv_len or not mask.is_contiguous():
+            raise ValueError("mask must be contiguous fp16 [b, q_len, kv_len]")
+        a.mask = mask.data_ptr()
+    a.logits, a.probs, a.out = logits.data_ptr(), probs.data_ptr(), out.data_ptr()
+    a.logits_stride_b, a.logits_stride_h, a.logits_stride_q = logits.stride(0), logits.stride(1), logits.stride(2)
+    with torch.cuda.device(q.device):
+        _lib.check(lib.spatten_prefill_attn(C.byref(a), C.c_void_p(_stream_ptr(q.device))))
+    return out, logits
+
+
 # ------------------------------------------------------------------------------------------------------
 # token pruning
 # ------------------------------------------------------------------------------------------------------

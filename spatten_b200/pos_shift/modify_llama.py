@@ -123,8 +123,14 @@ def llama_pos_shift_attention_forward(
         kbuf[:, :, past_len:kv_seq_len].copy_(k_new.transpose(1, 2))
         vbuf[:, :, past_len:kv_seq_len].copy_(v_new.transpose(1, 2))
         scores = torch.empty((bsz, H, q_len, kv_seq_len), dtype=torch.float16, device=dev)
-        out = ops.decode_attn(q, kbuf, vbuf, kv_seq_len, rope, q_pos=position_ids.reshape(bsz, q_len), mask=mask,
-                              logits=scores, head_mask=getattr(self, "spatten_head_mask", None))
+        head_mask = getattr(self, "spatten_head_mask", None)
+        if D == 128 and head_mask is None and q_len >= 16:
+            # dense tiles: Q.K^T and P.V on the tcgen05 tensor cores (spatten_prefill_attn)
+            out, _ = ops.prefill_attn(q, kbuf, vbuf, kv_seq_len, rope, position_ids.reshape(bsz, q_len), mask, scores)
+        else:
+            # short chunks / other head sizes / pruned heads: one decode-kernel row per (query, head)
+            out = ops.decode_attn(q, kbuf, vbuf, kv_seq_len, rope, q_pos=position_ids.reshape(bsz, q_len), mask=mask,
+                                  logits=scores, head_mask=head_mask)
     self.attn_scores = scores                                                        # :116-119 (pre-mask logits)
 
     attn_output = self.o_proj(out.view(bsz, q_len, H * D))                           # :146-163

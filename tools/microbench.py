@@ -122,6 +122,34 @@ def bench_extra(iters):
                       "frac_6445": round(kb / us / 1e3 / 6445, 4)}), flush=True)
 
 
+def bench_prefill(iters):
+    """Prefill attention core (tcgen05 path) for one Llama-2-7B layer: S x S causal, logits exported."""
+    dev, b, H, D = "cuda", 1, 32, 128
+    g = torch.Generator(device=dev).manual_seed(5)
+    for S in (1024, 4096, 8192):
+        q = torch.randn((b, S, H, D), generator=g, device=dev, dtype=torch.float16)
+        kc = torch.randn((b, H, S, D), generator=g, device=dev, dtype=torch.float16)
+        vc = torch.randn((b, H, S, D), generator=g, device=dev, dtype=torch.float16)
+        rope = ops.rope_table(D, S, dev)
+        pos = torch.arange(S, device=dev).unsqueeze(0)
+        mask = torch.full((S, S), torch.finfo(torch.float16).min, dtype=torch.float16, device=dev).triu(1)[None].contiguous()
+        logits = torch.empty((b, H, S, S), dtype=torch.float16, device=dev)
+        for _ in range(2):
+            ops.prefill_attn(q, kc, vc, S, rope, pos, mask, logits)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_it = max(2, iters // 10)
+        e0.record()
+        for _ in range(n_it):
+            ops.prefill_attn(q, kc, vc, S, rope, pos, mask, logits)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n_it
+        flops = 4.0 * S * S * H * D * b                      # both matmuls, dense (the reference computes the full square)
+        print(json.dumps({"kind": "prefill_umma", "S": S, "H": H, "ms_per_layer": round(ms, 3),
+                          "TFLOPs": round(flops / ms / 1e9, 1), "logits_GB": round(b * H * S * S * 2 / 1e9, 2)}), flush=True)
+
+
 def timeline(b, H, D, n, L, flags=0):
     """Phase timeline of the LAST of L back-to-back launches (warm caches), from %globaltimer stamps."""
     import ctypes as C
@@ -171,9 +199,13 @@ if __name__ == "__main__":
     ap.add_argument("--timeline", action="store_true", help="dump per-phase globaltimer stamps for one launch")
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--extra", action="store_true", help="config-4 quantised decode and Mode-B local-V timings")
+    ap.add_argument("--prefill", action="store_true", help="tcgen05 prefill attention timings")
     a = ap.parse_args()
     if a.extra:
         bench_extra(a.iters)
+        sys.exit(0)
+    if a.prefill:
+        bench_prefill(a.iters)
         sys.exit(0)
     if a.timeline:
         timeline(*map(int, (a.shape or "1,32,128,2048,32").split(",")), flags=a.flags)
