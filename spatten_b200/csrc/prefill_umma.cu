@@ -136,8 +136,11 @@ __global__ void __launch_bounds__(kUThreads) umma_qk_kernel(const PrefillParams 
 
   // producers: rows of Q (rotated at q_pos) and of K (rotated at the slot index), fp16 op for op (:21-28)
   const __half* Kc = p.k_cache + b * p.stride_b + kvh * p.stride_h;
-  for (int piece = tid; piece < kTileM * (kChunks / 2); piece += kUThreads) {
-    const int r = piece / (kChunks / 2), c = piece % (kChunks / 2);      // row, chunk of the FIRST half; partner c + kChunks/2
+  // work unit of a warp-iteration: 8 rows x 4 chunk pairs.  lane % 8 -> row, lane / 8 -> chunk: a quarter-warp writes
+  // one whole 128-byte core matrix (bank-conflict free) and each row is read as 64 contiguous bytes
+  static_assert(kChunks / 2 == 8, "producer mapping assumes head_dim 128");
+  for (int unit = warp; unit < (kTileM / 8) * 2; unit += kUThreads / 32) {
+    const int r = (unit >> 1) * 8 + (lane & 7), c = (unit & 1) * 4 + (lane >> 3);   // row, chunk of the FIRST half
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
       const int row = (which ? n0 : m0) + r;
@@ -188,24 +191,45 @@ __global__ void __launch_bounds__(kUThreads) umma_qk_kernel(const PrefillParams 
   mbar_wait_bounded(&s_bar, 0);
   tc_fence_after();
 
-  // epilogue: warp w owns rows 32w..32w+31 (TMEM lanes); fp16(acc) / sqrt(D) -> fp16 (:111-113)
-  const int row = m0 + warp * 32 + lane;
-  __half* dst = p.logits + b * p.ls_b + h * p.ls_h + static_cast<int64_t>(row) * p.ls_q + n0;
+  // epilogue: warp w owns rows 32w..32w+31 (TMEM lanes); fp16(acc) / sqrt(D) -> fp16 (:111-113).  The fp16 tile is
+  // staged in the (now idle) operand shared memory with a padded pitch and written out as whole 256-byte row
+  // segments, 16 lanes x 16 bytes per row.
+  constexpr int kPitch = kTileN * 2 + 16;              // bytes; +16 keeps the 16-byte stores of 32 rows off one bank group
+  uint8_t* sC = smem;                                   // 128 x 272 B = 34 KiB <= the two operand tiles
+  {
+    const int r = warp * 32 + lane;
 #pragma unroll 1
-  for (int cb = 0; cb < kTileN; cb += 32) {
-    float v[32];
-    tmem_ld32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + cb, v);
-    if (row < p.q_len) {
+    for (int cb = 0; cb < kTileN; cb += 32) {
+      float v[32];
+      tmem_ld32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + cb, v);
       __align__(16) __half o[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         o[i] = __float2half_rn(pf_div_by_const(__half2float(__float2half_rn(v[i])), p.sqrt_d, p.rsqrt_d));
-      if (n0 + cb + 32 <= p.kv_len && ((reinterpret_cast<uintptr_t>(dst + cb) & 15) == 0)) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(dst + cb)[i] = reinterpret_cast<const uint4*>(o)[i];
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<uint4*>(sC + r * kPitch + cb * 2 + i * 16) = reinterpret_cast<const uint4*>(o)[i];
+    }
+  }
+  __syncthreads();
+  {
+    __half* base = p.logits + b * p.ls_b + h * p.ls_h + n0;
+    const bool vec_ok = (p.ls_q % 8) == 0 && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+    const int half_w = lane >> 4, piece = lane & 15;    // 2 rows per warp instruction, 16 pieces of 8 logits per row
+#pragma unroll 1
+    for (int rr = warp * 2 + half_w; rr < kTileM; rr += 8) {
+      const int row = m0 + rr;
+      if (row >= p.q_len) continue;
+      const int col = piece * 8;
+      if (n0 + col >= p.kv_len) continue;
+      const uint4 val = *reinterpret_cast<const uint4*>(sC + rr * kPitch + col * 2);
+      __half* dst = base + static_cast<int64_t>(row) * p.ls_q + col;
+      if (vec_ok && n0 + col + 8 <= p.kv_len) {
+        *reinterpret_cast<uint4*>(dst) = val;
       } else {
-        for (int i = 0; i < 32; ++i)
-          if (n0 + cb + i < p.kv_len) dst[cb + i] = o[i];
+        const __half* hv = reinterpret_cast<const __half*>(&val);
+        for (int i = 0; i < 8; ++i)
+          if (n0 + col + i < p.kv_len) dst[i] = hv[i];
       }
     }
   }
@@ -215,8 +239,26 @@ __global__ void __launch_bounds__(kUThreads) umma_qk_kernel(const PrefillParams 
 }
 
 // ---- 2. P = softmax(S + mask), fp32 (:132-137) ---------------------------------------------------------------------
-// one warp per (b, h, q) row
-__global__ void softmax_rows_kernel(const PrefillParams p) {
+// one warp per (b, h, q) row.  Pass 1 reads the row once with 128-bit loads and keeps a running (max, sum) per lane
+// (online softmax, so no row-sized register array and full occupancy); pass 2 re-reads it -- an L2 hit, the row
+// was touched microseconds ago -- and writes the fp16 probabilities.
+__device__ __forceinline__ void sm_load8(const __half* s, const __half* mk, int j, float (&f)[8]) {
+  uint4 x = *reinterpret_cast<const uint4*>(s + j);
+  __half2* h2 = reinterpret_cast<__half2*>(&x);
+  if (mk) {
+    const uint4 mm = __ldg(reinterpret_cast<const uint4*>(mk + j));
+    const __half2* m2 = reinterpret_cast<const __half2*>(&mm);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h2[e] = __hadd2_rn(h2[e], m2[e]);      // fp16 add, as attn_weights + attention_mask (:132)
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 t = __half22float2(h2[e]);
+    f[2 * e] = t.x; f[2 * e + 1] = t.y;
+  }
+}
+
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const PrefillParams p) {
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int64_t rows = static_cast<int64_t>(p.batch) * p.H * p.q_len;
@@ -225,25 +267,51 @@ __global__ void softmax_rows_kernel(const PrefillParams p) {
   const __half* s = p.logits + b * p.ls_b + h * p.ls_h + static_cast<int64_t>(qi) * p.ls_q;
   __half* o = p.probs + b * p.ls_b + h * p.ls_h + static_cast<int64_t>(qi) * p.ls_q;
   const __half* mk = p.mask ? p.mask + (static_cast<int64_t>(b) * p.q_len + qi) * p.kv_len : nullptr;
-  float mx = -CUDART_INF_F;
-  for (int j = lane; j < p.kv_len; j += 32) {
-    __half x = s[j];
-    if (mk) x = __hadd_rn(x, mk[j]);
-    mx = fmaxf(mx, __half2float(x));
+  const bool vec = (p.kv_len % 8) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(o) | reinterpret_cast<uintptr_t>(mk)) & 15) == 0;
+  float mx = -CUDART_INF_F, sum = 0.f;
+  if (vec) {
+    for (int j = lane * 8; j < p.kv_len; j += 256) {
+      float f[8];
+      sm_load8(s, mk, j, f);
+      float m8 = f[0];
+#pragma unroll
+      for (int e = 1; e < 8; ++e) m8 = fmaxf(m8, f[e]);
+      const float m_new = fmaxf(mx, m8);
+      float part = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) part += __expf(f[e] - m_new);
+      sum = sum * __expf(mx - m_new) + part;
+      mx = m_new;
+    }
+  } else {
+    for (int j = lane; j < p.kv_len; j += 32) {
+      __half x = s[j];
+      if (mk) x = __hadd_rn(x, mk[j]);
+      const float v = __half2float(x), m_new = fmaxf(mx, v);
+      sum = sum * __expf(mx - m_new) + __expf(v - m_new);
+      mx = m_new;
+    }
   }
-  mx = warp_max(mx);
-  float sum = 0.f;
-  for (int j = lane; j < p.kv_len; j += 32) {
-    __half x = s[j];
-    if (mk) x = __hadd_rn(x, mk[j]);
-    sum += __expf(__half2float(x) - mx);
-  }
-  sum = warp_sum(sum);
+  const float M = warp_max(mx);
+  sum = warp_sum(sum * __expf(mx - M));
   const float inv = 1.f / sum;
-  for (int j = lane; j < p.kv_len; j += 32) {
-    __half x = s[j];
-    if (mk) x = __hadd_rn(x, mk[j]);
-    o[j] = __float2half_rn(__expf(__half2float(x) - mx) * inv);
+  if (vec) {
+    for (int j = lane * 8; j < p.kv_len; j += 256) {
+      float f[8];
+      sm_load8(s, mk, j, f);
+      uint4 outv;
+      __half2* h2 = reinterpret_cast<__half2*>(&outv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(__expf(f[2 * e] - M) * inv, __expf(f[2 * e + 1] - M) * inv);
+      *reinterpret_cast<uint4*>(o + j) = outv;
+    }
+  } else {
+    for (int j = lane; j < p.kv_len; j += 32) {
+      __half x = s[j];
+      if (mk) x = __hadd_rn(x, mk[j]);
+      o[j] = __float2half_rn(__expf(__half2float(x) - M) * inv);
+    }
   }
 }
 
@@ -257,6 +325,7 @@ __global__ void __launch_bounds__(kUThreads) umma_pv_kernel(const PrefillParams 
   constexpr int kABytes = kTileM * BK * 2;              // 16 KiB
   constexpr int kBBytes = BK * D * 2;                   // 16 KiB (D = 128)
   constexpr int kNChunks = D / 8;                       // 16-byte chunks along D
+  static_assert(D == 128 && kTileM * kAChunks == 32 * 32 && BK * kNChunks == 32 * 32, "producer mapping assumes these tiles");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + kABytes;
@@ -275,13 +344,17 @@ __global__ void __launch_bounds__(kUThreads) umma_pv_kernel(const PrefillParams 
   const __half* P = p.probs + b * p.ls_b + h * p.ls_h;
   const __half* V = p.v_cache + b * p.stride_b + kvh * p.stride_h;
   const bool vec_ok = (p.ls_q % 8) == 0 && ((reinterpret_cast<uintptr_t>(P) & 15) == 0);
-  uint32_t phase = 0;
   const int nk = (p.kv_len + BK - 1) / BK;
-  for (int kb = 0; kb < nk; ++kb) {
+  constexpr int kAPer = kTileM * kAChunks / kUThreads;      // 8 x 16-byte pieces of P per thread per block
+  constexpr int kBPer = BK * kNChunks / kUThreads;          // 8 x 16-byte pieces of V per thread per block
+  uint4 ra[kAPer], rb[kBPer];
+  // global -> registers for K block kb (software pipelining: issued while the tensor core works on block kb-1)
+  auto fetch = [&](int kb) {
     const int k0 = kb * BK;
-    // A: P[m0 + r, k0 + 8c .. +8)
-    for (int piece = tid; piece < kTileM * kAChunks; piece += kUThreads) {
-      const int r = piece / kAChunks, c = piece % kAChunks;
+#pragma unroll
+    for (int i = 0; i < kAPer; ++i) {
+      const int unit = warp + i * (kUThreads / 32);                    // 8 rows x 4 chunks per warp-iteration
+      const int r = (unit >> 1) * 8 + (lane & 7), c = (unit & 1) * 4 + (lane >> 3);
       uint4 val = make_uint4(0, 0, 0, 0);
       const int row = m0 + r, col = k0 + c * 8;
       if (row < p.q_len && col < p.kv_len) {
@@ -291,18 +364,38 @@ __global__ void __launch_bounds__(kUThreads) umma_pv_kernel(const PrefillParams 
         } else {
           __align__(16) __half t[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) t[i] = (col + i < p.kv_len) ? src[i] : __float2half(0.f);
+          for (int e = 0; e < 8; ++e) t[e] = (col + e < p.kv_len) ? src[e] : __float2half(0.f);
           val = *reinterpret_cast<const uint4*>(t);
         }
       }
-      *reinterpret_cast<uint4*>(sA + kmajor_off(r, c, kAChunks)) = val;
+      ra[i] = val;
     }
-    // B: V[k0 + j, 8c .. +8): core matrix (token group j/8, D chunk c) at (j/8) * LBO + c * SBO, row j%8 inside
-    for (int piece = tid; piece < BK * kNChunks; piece += kUThreads) {
-      const int j = piece / kNChunks, c = piece % kNChunks;
-      uint4 val = make_uint4(0, 0, 0, 0);
-      if (k0 + j < p.kv_len) val = *reinterpret_cast<const uint4*>(V + static_cast<int64_t>(k0 + j) * D + c * 8);
-      *reinterpret_cast<uint4*>(sB + (j >> 3) * (kNChunks * 128) + c * 128 + (j & 7) * 16) = val;
+#pragma unroll
+    for (int i = 0; i < kBPer; ++i) {
+      const int unit = warp + i * (kUThreads / 32);                    // 8 tokens x 4 D-chunks per warp-iteration
+      const int j = (unit >> 2) * 8 + (lane & 7), c = (unit & 3) * 4 + (lane >> 3);
+      rb[i] = (k0 + j < p.kv_len) ? *reinterpret_cast<const uint4*>(V + static_cast<int64_t>(k0 + j) * D + c * 8)
+                                  : make_uint4(0, 0, 0, 0);
+    }
+  };
+  fetch(0);
+  for (int kb = 0; kb < nk; ++kb) {
+    if (kb > 0) {                       // the MMAs of block kb-1 have consumed shared memory
+      mbar_wait_bounded(&s_bar, (kb - 1) & 1);
+      tc_fence_after();
+    }
+    // A: P[m0 + r, k0 + 8c .. +8) K-major;  B: V[k0 + j, 8c .. +8) MN-major: core matrix (token group j/8, D chunk c)
+    // at (j/8) * LBO + c * SBO, row j%8 inside
+#pragma unroll
+    for (int i = 0; i < kAPer; ++i) {
+      const int unit = warp + i * (kUThreads / 32);
+      *reinterpret_cast<uint4*>(sA + kmajor_off((unit >> 1) * 8 + (lane & 7), (unit & 1) * 4 + (lane >> 3), kAChunks)) = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < kBPer; ++i) {
+      const int unit = warp + i * (kUThreads / 32);
+      const int j = (unit >> 2) * 8 + (lane & 7), c = (unit & 3) * 4 + (lane >> 3);
+      *reinterpret_cast<uint4*>(sB + (j >> 3) * (kNChunks * 128) + c * 128 + (j & 7) * 16) = rb[i];
     }
     fence_proxy_async();
     tc_fence_before();
@@ -319,10 +412,10 @@ __global__ void __launch_bounds__(kUThreads) umma_pv_kernel(const PrefillParams 
       }
       umma_commit(&s_bar);
     }
-    mbar_wait_bounded(&s_bar, phase);           // the MMAs have consumed this block: shared memory may be overwritten
-    phase ^= 1;
-    tc_fence_after();
+    if (kb + 1 < nk) fetch(kb + 1);     // in flight while the tensor core runs block kb
   }
+  mbar_wait_bounded(&s_bar, (nk - 1) & 1);
+  tc_fence_after();
 
   const int row = m0 + warp * 32 + lane;
   __half* dst = p.out + ((static_cast<int64_t>(b) * p.q_len + row) * p.H + h) * D;
