@@ -242,7 +242,14 @@ def run_ours(args):
     px = None
     if world > 1 and args.collective == "fused":
         # attention output stored straight into every peer's gather buffer by the kernel; no collective kernel
-        px = PeerExchange(L, shard, b, D, dev)
+        try:
+            px = PeerExchange(L, shard, b, D, dev)
+        except Exception as e:              # no peer-mappable memory on this box: use the NCCL formulation, and say so
+            if rank == 0:
+                print(f"[bench] symmetric memory unavailable ({type(e).__name__}: {e}); falling back to NCCL all-reduce",
+                      file=sys.stderr)
+            args.collective = "allreduce"
+    if px is not None:
         gathered = px.gathered
         for l in range(L):
             # layer l waits, inside its own kernel, for layer l-1's exchange; one wait launch closes the step

@@ -22,9 +22,9 @@
 
 namespace spatten {
 
-constexpr int kQWarps = 8;
+constexpr int kQWarps = 16;     // the dequantise-rotate-dot loop is ALU heavy: 16 warps per SM hide its latencies
 constexpr int kQThreads = kQWarps * 32;
-constexpr int kQTile = 32;      // tokens per stage (per warp)
+constexpr int kQTile = 16;      // tokens per stage (per warp): 4 planes x 1 KiB + scales, 3 stages -> 200 KiB per CTA
 constexpr int kQStages = 3;
 constexpr int kQMaxPartials = 8192;
 constexpr float kLog2eQ = 1.4426950408889634f;
@@ -167,15 +167,18 @@ __global__ void __launch_bounds__(kQThreads, 1) decode_attn_q4_kernel(const Quan
 #pragma unroll 1
     for (int sub = 0; sub < kQTile; sub += 16) {
       if (sub >= ntok) break;
-      float sc[4], vs[4];
+      float sc[4], vs[4], d[4];
+      // RoPE rows of the 4 passes first (independent global loads), then the 4 independent dot-product chains
+      uint4 cs4[4], sn4[4];
+#pragma unroll
+      for (int ps = 0; ps < 4; ++ps) {
+        const int jr = min(tok0 + sub + ps * 4 + g, p.rope_len - 1);
+        cs4[ps] = __ldg(reinterpret_cast<const uint4*>(p.rope + static_cast<int64_t>(jr) * D + c * 8));
+        sn4[ps] = __ldg(reinterpret_cast<const uint4*>(p.rope + static_cast<int64_t>(jr) * D + 64 + c * 8));
+      }
 #pragma unroll
       for (int ps = 0; ps < 4; ++ps) {
         const int tl = sub + ps * 4 + g;
-        const int j = tok0 + tl;
-        const bool valid = tl < ntok;
-        const int jr = min(j, p.rope_len - 1);
-        const uint4 cs = __ldg(reinterpret_cast<const uint4*>(p.rope + static_cast<int64_t>(jr) * D + c * 8));
-        const uint4 sn = __ldg(reinterpret_cast<const uint4*>(p.rope + static_cast<int64_t>(jr) * D + 64 + c * 8));
         const uint32_t wml = *reinterpret_cast<const uint32_t*>(st + tl * kPlaneRow + c * 4);
         const uint32_t wmh = *reinterpret_cast<const uint32_t*>(st + tl * kPlaneRow + 32 + c * 4);
         uint32_t wll = 0, wlh = 0;
@@ -186,8 +189,8 @@ __global__ void __launch_bounds__(kQThreads, 1) decode_attn_q4_kernel(const Quan
         __half2 kl[4], kh[4];
         deq8<LSB>(wml, wll, kl);
         deq8<LSB>(wmh, wlh, kh);
-        const __half2* c2 = reinterpret_cast<const __half2*>(&cs);
-        const __half2* s2 = reinterpret_cast<const __half2*>(&sn);
+        const __half2* c2 = reinterpret_cast<const __half2*>(&cs4[ps]);
+        const __half2* s2 = reinterpret_cast<const __half2*>(&sn4[ps]);
         float d0 = 0.f, d1 = 0.f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -196,13 +199,21 @@ __global__ void __launch_bounds__(kQThreads, 1) decode_attn_q4_kernel(const Quan
           d0 = fmaf(ql[2 * e], fl.x, d0); d0 = fmaf(ql[2 * e + 1], fl.y, d0);
           d1 = fmaf(qh[2 * e], fh.x, d1); d1 = fmaf(qh[2 * e + 1], fh.y, d1);
         }
-        float d = d0 + d1;
-        d += __shfl_xor_sync(0xffffffffu, d, 1);
-        d += __shfl_xor_sync(0xffffffffu, d, 2);
-        d += __shfl_xor_sync(0xffffffffu, d, 4);
+        d[ps] = d0 + d1;
+      }
+#pragma unroll
+      for (int o = 1; o <= 4; o <<= 1) {
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) d[ps] += __shfl_xor_sync(0xffffffffu, d[ps], o);
+      }
+#pragma unroll
+      for (int ps = 0; ps < 4; ++ps) {
+        const int tl = sub + ps * 4 + g;
+        const int j = tok0 + tl;
+        const bool valid = tl < ntok;
         const float ks = valid ? __half2float(*reinterpret_cast<const __half*>(st + 4 * kPlaneTile + tl * 2)) : 0.f;
         vs[ps] = valid ? __half2float(*reinterpret_cast<const __half*>(st + 4 * kPlaneTile + kScaleTile + tl * 2)) : 0.f;
-        const __half s16 = __float2half_rn(q_div_by_const(__half2float(__float2half_rn(d * ks)), p.sqrt_d, p.rsqrt_d));
+        const __half s16 = __float2half_rn(q_div_by_const(__half2float(__float2half_rn(d[ps] * ks)), p.sqrt_d, p.rsqrt_d));
         if (valid && c == 0 && lg) lg[j] = s16;
         sc[ps] = valid ? __half2float(s16) : -CUDART_INF_F;
       }
@@ -282,12 +293,28 @@ __global__ void quant_merge_kernel(const QuantDecodeParams p) {
   for (int s = lane; s < p.n_splits; s += 32) M = fmaxf(M, ml[s].x);
   M = warp_max(M);
   float L = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int s = 0; s < p.n_splits; ++s) {
+  for (int s = lane; s < p.n_splits; s += 32) {
     const float2 v = ml[s];
-    const float w = (M > -CUDART_INF_F) ? fast_exp2((v.x - M) * kLog2eQ) : 0.f;
-    L = fmaf(v.y, w, L);
-    const float4 a = *reinterpret_cast<const float4*>(rec + static_cast<int64_t>(s) * D + lane * 4);
-    o[0] = fmaf(a.x, w, o[0]); o[1] = fmaf(a.y, w, o[1]); o[2] = fmaf(a.z, w, o[2]); o[3] = fmaf(a.w, w, o[3]);
+    L = fmaf(v.y, (M > -CUDART_INF_F) ? fast_exp2((v.x - M) * kLog2eQ) : 0.f, L);
+  }
+  L = warp_sum(L);
+  // partial outputs: 8 independent 16-byte loads in flight per lane (the loop is latency bound otherwise)
+#pragma unroll 1
+  for (int s0 = 0; s0 < p.n_splits; s0 += 8) {
+    float4 a[8];
+    float w[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int s = min(s0 + u, p.n_splits - 1);
+      a[u] = *reinterpret_cast<const float4*>(rec + static_cast<int64_t>(s) * D + lane * 4);
+      const float mv = ml[s].x;
+      w[u] = (s0 + u < p.n_splits && M > -CUDART_INF_F) ? fast_exp2((mv - M) * kLog2eQ) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      o[0] = fmaf(a[u].x, w[u], o[0]); o[1] = fmaf(a[u].y, w[u], o[1]);
+      o[2] = fmaf(a[u].z, w[u], o[2]); o[3] = fmaf(a[u].w, w[u], o[3]);
+    }
   }
   const float inv = L > 0.f ? 1.f / L : 0.f;
   __half2 r0 = __floats2half2_rn(o[0] * inv, o[1] * inv), r1 = __floats2half2_rn(o[2] * inv, o[3] * inv);
@@ -415,21 +442,21 @@ extern "C" int spatten_decode_attn_quant(const SpattenQuantDecodeArgs* a, void* 
 
   const int sms = sm_count();
   if (sms <= 0) return SPATTEN_ERR_CUDA;
-  p.rpc = p.rows >= 8 ? 8 : (p.rows >= 4 ? 4 : (p.rows >= 2 ? 2 : 1));
+  p.rpc = p.rows >= 8 ? 8 : (p.rows >= 4 ? 4 : (p.rows >= 2 ? 2 : 1));   // rows per CTA; the other warps split tokens
   p.spc = kQWarps / p.rpc;
   p.n_rg = (p.rows + p.rpc - 1) / p.rpc;
-  // ranges: fill the SMs once; every warp gets a multiple of 32 tokens (scale rows are fetched in 16-byte granules)
+  // ranges: fill the SMs once; every warp gets a multiple of kQTile tokens (scale rows are fetched in 16-byte granules)
   int best = 1; long best_cost = -1;
   const int max_ranges = std::max(1, std::min({(a->kv_len + p.spc * 32 - 1) / (p.spc * 32),
                                                kQMaxPartials / (p.n_rg * p.rpc * p.spc), 256 / p.spc}));
   for (int nr = 1; nr <= max_ranges; ++nr) {
     const long waves = (static_cast<long>(p.n_rg) * nr + sms - 1) / sms;
-    const int tps = ((a->kv_len + nr * p.spc - 1) / (nr * p.spc) + 31) / 32 * 32;
+    const int tps = ((a->kv_len + nr * p.spc - 1) / (nr * p.spc) + kQTile - 1) / kQTile * kQTile;
     const long cost = waves * (tps + 48);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = nr; }
   }
   p.n_splits = best * p.spc;
-  p.tok_per_split = ((a->kv_len + p.n_splits - 1) / p.n_splits + 31) / 32 * 32;
+  p.tok_per_split = ((a->kv_len + p.n_splits - 1) / p.n_splits + kQTile - 1) / kQTile * kQTile;
   SPATTEN_CHECK_ARG(a->workspace_bytes >= spatten_decode_quant_workspace_bytes(a->batch, a->num_heads, a->head_dim),
                     "spatten_decode_attn_quant: workspace too small");
   p.part_ml = static_cast<float2*>(a->workspace);
