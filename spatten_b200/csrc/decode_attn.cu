@@ -177,6 +177,11 @@ __global__ void __launch_bounds__(kThreads, kPasses == 2 ? 2 : 1) decode_attn_ke
   uint8_t* wsm = smem + warp * kWarpSmem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWarps * kWarpSmem) + warp * kStages;
 
+  // Cluster mode writes into peer CTAs' shared memory at the end.  That is only legal once every CTA of the cluster
+  // has started, so everyone arrives on the cluster barrier here and waits for it right before the first push --
+  // by then the arrival is seconds-old in GPU terms and the wait is free (compute-sanitizer racecheck clean).
+  if constexpr (MODE == 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+
   // Programmatic dependent launch: let the next kernel in the stream start its own prologue early ...
   if (p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // ... and, unless the caller vouches that the cached K/V rows and the RoPE table are older than any
@@ -424,7 +429,7 @@ __global__ void __launch_bounds__(kThreads, kPasses == 2 ? 2 : 1) decode_attn_ke
   }
   STAMP(3);   // streaming loop done
   if (p.scores_only) {
-    if constexpr (MODE == 1) cluster_sync_all();   // cluster CTAs leave together
+    if constexpr (MODE == 1) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");   // pairs with the entry arrive
     return;
   }
 
@@ -445,6 +450,7 @@ __global__ void __launch_bounds__(kThreads, kPasses == 2 ? 2 : 1) decode_attn_ke
     // slice of D.  Every warp PUSHES its partial into the receive buffers of those CTAs (st.shared::cluster,
     // fire and forget), one cluster barrier publishes them, and each CTA then merges from its own shared memory
     // and exits -- no remote loads, no second barrier.
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");   // every CTA of the cluster is running (entry arrive)
     const int ds_sh = p.ds_shift;                       // DS = D * rpc / cluster is a power of two
     const int DS = 1 << ds_sh;                          // dims per merging CTA
     float* recv = reinterpret_cast<float*>(smem + kWarps * kWarpSmem + kWarps * kStages * 8);  // [n_splits][DS + 2]
