@@ -521,15 +521,24 @@ __global__ void __launch_bounds__(kThreads, kPasses == 2 ? 2 : 1) decode_attn_ke
 #pragma unroll
             for (int i = 0; i < 4; ++i) o[i] += __shfl_xor_sync(0xffffffffu, o[i], sft);
           }
-          if (lane < 4 && d0 + lane < DW) {
-            const float mine = lane == 0 ? o[0] : (lane == 1 ? o[1] : (lane == 2 ? o[2] : o[3]));
-            const __half o16 = __float2half_rn(mine * inv);
-            store_out(p, static_cast<int64_t>(mrow) * D + slice * DS + warp * DW + d0 + lane, o16);
-            habs += fabsf(__half2float(o16));
+          if (lane == 0) {                                 // the butterflies left all four sums in every lane
+            const __half2 x01 = __floats2half2_rn(o[0] * inv, o[1] * inv), x23 = __floats2half2_rn(o[2] * inv, o[3] * inv);
+            const int64_t off = static_cast<int64_t>(mrow) * D + slice * DS + warp * DW + d0;
+            if (d0 + 4 <= DW) {                              // one 8-byte store per peer instead of four 2-byte ones
+              uint2 pk;
+              pk.x = *reinterpret_cast<const uint32_t*>(&x01);
+              pk.y = *reinterpret_cast<const uint32_t*>(&x23);
+              store_out(p, off, pk);
+            } else {
+              const __half xs[4] = {__low2half(x01), __high2half(x01), __low2half(x23), __high2half(x23)};
+              for (int i = 0; d0 + i < DW; ++i) store_out(p, off + i, xs[i]);
+            }
+            const float2 f01 = __half22float2(x01), f23 = __half22float2(x23);
+            habs += fabsf(f01.x) + fabsf(f01.y);
+            if (d0 + 2 < DW) habs += fabsf(f23.x) + fabsf(f23.y);
           }
         }
         if (p.head_importance) {
-          habs = warp_sum(habs);
           if (lane == 0) atomicAdd(p.head_importance + (mrow % p.H), habs);
         }
         if (slice == 0 && p.importance && p.logits && M > -CUDART_INF_F) {
