@@ -249,6 +249,7 @@ def run_ours(args):
                 print(f"[bench] symmetric memory unavailable ({type(e).__name__}: {e}); falling back to NCCL all-reduce",
                       file=sys.stderr)
             args.collective = "allreduce"
+    local_out = gathered       # `local_args` (kernel-only roofline region) keep writing here: it must stay allocated
     if px is not None:
         gathered = px.gathered
         for l in range(L):
@@ -456,6 +457,7 @@ def run_ours(args):
                 if px is not None else f"nccl {args.collective} of [N={world}, b={b}, H/N={Hl}, D={D}] fp16 per layer"),
             "peer_wait_timed_out": px.timed_out() if px is not None else None,
             "pdl": bool(flags),
+            "local_out_bytes": local_out.numel() * 2,
         }
         line.update(extras)
         print(json.dumps(line), flush=True)
