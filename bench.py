@@ -184,7 +184,7 @@ class ClockSampler:
 
 def run_ours(args):
     import faulthandler
-    faulthandler.dump_traceback_later(150, exit=True)      # a wedged collective must not eat the GPU lease
+    faulthandler.dump_traceback_later(900, exit=True)      # a wedged collective must not eat the GPU lease
     import torch
     import torch.distributed as dist
     from spatten_b200 import _lib, ops
