@@ -7,14 +7,19 @@
 // Work decomposition (B200: 148 SMs, HBM-bound GEMV-class scan):
 //   * a CTA is 8 independent warps; warp w owns one (batch, head) row and one contiguous token range,
 //     streams that range's K and V rows HBM -> shared memory with 1-D bulk async copies (TMA engine,
-//     cp.async.bulk + mbarrier complete_tx) through a private 6-stage ring, and keeps its own online
-//     softmax state (m, l, acc[D]) in registers.  No CTA-wide barrier in the streaming loop.
-//   * the 8 warps of a CTA work on the SAME token range of 8 different rows, so the RoPE table rows
-//     (shared by all heads) are fetched from L2 once and hit L1 for the other 7 warps.
-//   * the grid is sized to ~one CTA per SM; the host picks the number of token ranges so that
-//     (row groups) x (ranges) fills the SMs evenly.
-//   * each warp writes an (acc, m, l) partial; the last CTA to finish a row group (atomic ticket) merges
-//     the partials, writes fp16 out, and optionally accumulates token / head importance.
+//     cp.async.bulk + mbarrier complete_tx) through a private 3-stage ring of 16-token tiles, and keeps its
+//     own online softmax state (m, l, acc[D]) in registers.  No CTA-wide barrier in the streaming loop.
+//   * the appended token is folded into the tile loop (dropped into the tile in shared memory and into the
+//     cache slot), so there is no append kernel and no second code path.
+//   * two ways to merge the splits of a row, picked per launch by the host (see spatten_decode_attn below):
+//       MODE 1 "cluster": all splits of a row live in one thread-block cluster (4 or 8 CTAs); every warp pushes
+//         its (acc, m, l) slices into the finishing CTAs' shared memory (DSMEM), one cluster barrier, local merge.
+//       MODE 0 "ticket": grid = (row groups) x (token ranges) sized to one wave; the 8 warps of a CTA take the
+//         same token range of 8 rows (RoPE rows hit L1); partials go to a workspace and a per-row atomic ticket
+//         elects the last warp, which merges with all partial loads in flight at once.
+//   * optional: programmatic dependent launch with the K/V prefetch ahead of griddepcontrol.wait; fused output
+//     exchange for head sharding (stores into every peer GPU's gather buffer + flag; consumer wait folded in
+//     before the query load); token / head importance accumulation; head mask; scores-only mode.
 //
 // Tensor cores are deliberately not used here: Llama-2 7B/13B are MHA, so each KV row meets exactly one
 // query row (M = 1); a tcgen05 tile would be >= 63/64 padding and the roofline is HBM bytes, not flops.
