@@ -37,7 +37,15 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "decode tok/s Llama-2-7B seq=4K 50% KV-prune (attention hot path, all layers)"
+def _baseline_metric():
+    """BASELINE.json's metric string, verbatim; the step definition lives in config.workload."""
+    try:
+        return json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
+    except Exception:
+        return "decode tok/s Llama-2-7B seq=4K 50% KV-prune; attn HBM GB/s vs peak at 1/2/4/8 GPU"
+
+
+METRIC = _baseline_metric()
 UNIT = "tok/s"
 # BASELINE.json configs[1]: Llama-2-7B decode bs=1 seq=4K, 50 % KV-token prune, fp16
 MODEL = dict(name="llama-2-7b", L=32, H=32, D=128, seq=4096, start=4, important=1022, recent=1022)
