@@ -152,6 +152,73 @@ int spatten_decode_attn_host(const SpattenDecodeArgs* args, const void* q_host, 
                              const void* v_new_host, void* out_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Decode STEP: the attention core of every layer of one decode token in ONE persistent launch.
+ *
+ * Same per-layer function as spatten_decode_attn (modify_llama.py:86-144 for q_len == 1, no mask -- HF 4.33
+ * builds an all-zero mask for a decode step), applied to `num_layers` layers that share one shape.  One CTA
+ * per SM stays resident for the whole step; every layer's (row, 16-token tile) work list is cut into equal
+ * contiguous ranges over all warps of the grid, and each warp's bulk-copy ring runs ahead ACROSS layer
+ * boundaries, so the K/V stream of layer l+1 is already in flight while layer l is being merged -- the
+ * per-launch latency (launch, first byte, merge tail) that bounds a 5 us per-layer kernel is paid once per
+ * step instead of once per layer.  The K/V cache rows of a layer do not depend on the previous layer; only the
+ * query does, and that dependency is kept when asked for:
+ *
+ *   SPATTEN_STEP_CHAIN  a warp reads the query (and k_new / v_new) of layer l+1 only after EVERY row of layer l
+ *                       has been merged and stored (per-layer completion flags, release/acquire at GPU scope) --
+ *                       the ordering a decoder imposes (the next layer's q is a function of all heads of this
+ *                       one).  K/V prefetch of layer l+1 still overlaps.  With n_peers > 0 the chain runs over the
+ *                       fused exchange instead: layer l+1 waits until all n_peers ranks have delivered layer l.
+ *
+ * Split-KV partials go through a workspace and per-(layer, row) tickets; the last warp of a row merges it.
+ * Outputs: layers[l].out (or, n_peers > 0, every peer's gather buffer), layers[l].logits, optional importance /
+ * head_importance as in spatten_decode_attn.  head_mask is per layer: u8 [num_layers, num_heads] (<= 64 heads);
+ * pruned heads cost no KV traffic and no work slot, their output rows are zeroed, and the appended K/V row is
+ * still written (by the first live head of the kv group, or by the zeroing warp when the whole group is pruned).
+ * ---------------------------------------------------------------------------------------------- */
+#define SPATTEN_STEP_CHAIN 1u
+
+typedef struct SpattenStepLayer {   /* one per layer, array in DEVICE memory */
+  const void* q;          /* fp16 [b, H, D] un-rotated */
+  const void* k_new;      /* fp16 [b, H_kv, D] (append == 1) */
+  const void* v_new;
+  void* k_cache;          /* fp16 [b, H_kv, >= kv_len + append, D] */
+  void* v_cache;
+  void* out;              /* fp16 [b, H, D] (n_peers == 0) */
+  void* logits;           /* optional fp16 [b, H, logits_stride] */
+  float* importance;      /* optional fp32 [b, H, importance_stride], += softmax probability (needs logits) */
+} SpattenStepLayer;
+
+typedef struct SpattenStepArgs {
+  uint32_t struct_size;
+  int32_t num_layers, batch, num_heads, num_kv_heads, head_dim;
+  int32_t kv_len, rope_len, append;     /* as in SpattenDecodeArgs, the same for every layer */
+  uint32_t flags;                       /* SPATTEN_STEP_* */
+  const SpattenStepLayer* layers;       /* DEVICE pointer to num_layers descriptors */
+  int64_t cache_stride_b, cache_stride_h;   /* elements */
+  int64_t logits_stride, importance_stride; /* elements between heads */
+  const void* rope;                     /* fp16 [rope_len, D] */
+  const int64_t* q_pos;                 /* [b] or NULL = kv_len */
+  const uint8_t* head_mask;             /* optional [num_layers, num_heads] */
+  float* head_importance;               /* optional fp32 [num_heads], += sum_d |out| over all layers */
+  /* fused exchange (head sharding), as in SpattenDecodeArgs but addressed per layer:
+   * layer l's rows go to peer_out[r] + l * peer_layer_stride (elements) on every peer r, and every finished row
+   * adds 1 to the u32 at peer_flags[r] + l * peer_flag_layer_stride (words).  wait_flags is THIS rank's own flag
+   * array [num_layers][n_peers] (the words the peers increment); the kernel waits on it between layers
+   * (SPATTEN_STEP_CHAIN) and, for the last layer, before it exits -- when the launch completes, every rank's rows
+   * of every layer are in the local gather buffer. */
+  int32_t n_peers;
+  void* peer_out[8];
+  int64_t peer_layer_stride;
+  void* peer_flags[8];
+  int64_t peer_flag_layer_stride;
+  const void* wait_flags;
+  void* workspace;                      /* >= spatten_decode_step_workspace_bytes(...), zero-filled ONCE */
+  size_t workspace_bytes;               /* u32 word 0: steps completed; word 2: set to 1 if a flag wait timed out */
+} SpattenStepArgs;
+size_t spatten_decode_step_workspace_bytes(int32_t num_layers, int32_t batch, int32_t num_heads, int32_t head_dim);
+int spatten_decode_step(const SpattenStepArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Prefill attention (q_len > 1) on the tcgen05 tensor cores.  Same reference lines as spatten_decode_attn
  * (modify_llama.py:86-144) in the reference's own three steps, because the full pre-mask logit matrix is an
  * output (`self.attn_scores`, :116-119): S = rope(Q).rope(K)^T (UMMA, RoPE fused into the operand staging,

@@ -18,6 +18,7 @@ DECODE_PDL_KV_STABLE = 2
 DECODE_NO_CLUSTER = 4
 DECODE_SCORES_ONLY = 8
 DECODE_SMALL_TILES = 16
+STEP_CHAIN = 1
 ERR_NAMES = {-1: "SPATTEN_ERR_INVALID", -2: "SPATTEN_ERR_UNSUPPORTED", -3: "SPATTEN_ERR_CUDA",
              -4: "SPATTEN_ERR_WORKSPACE"}
 
@@ -44,6 +45,29 @@ class DecodeArgs(C.Structure):
         ("n_peers", C.c_int32), ("peer_out", C.c_void_p * 8), ("peer_flags", C.c_void_p * 8),
         ("done_counter", C.c_void_p),
         ("wait_n", C.c_int32), ("wait_flags", C.c_void_p), ("wait_expected", C.c_void_p), ("wait_timeout", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+class StepLayer(C.Structure):
+    """Mirror of `SpattenStepLayer` (64 bytes; the array lives in device memory)."""
+    _fields_ = [("q", C.c_void_p), ("k_new", C.c_void_p), ("v_new", C.c_void_p), ("k_cache", C.c_void_p),
+                ("v_cache", C.c_void_p), ("out", C.c_void_p), ("logits", C.c_void_p), ("importance", C.c_void_p)]
+
+
+class StepArgs(C.Structure):
+    """Mirror of `SpattenStepArgs`."""
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("num_layers", C.c_int32), ("batch", C.c_int32), ("num_heads", C.c_int32), ("num_kv_heads", C.c_int32),
+        ("head_dim", C.c_int32), ("kv_len", C.c_int32), ("rope_len", C.c_int32), ("append", C.c_int32),
+        ("flags", C.c_uint32),
+        ("layers", C.c_void_p),
+        ("cache_stride_b", C.c_int64), ("cache_stride_h", C.c_int64),
+        ("logits_stride", C.c_int64), ("importance_stride", C.c_int64),
+        ("rope", C.c_void_p), ("q_pos", C.c_void_p), ("head_mask", C.c_void_p), ("head_importance", C.c_void_p),
+        ("n_peers", C.c_int32), ("peer_out", C.c_void_p * 8), ("peer_layer_stride", C.c_int64),
+        ("peer_flags", C.c_void_p * 8), ("peer_flag_layer_stride", C.c_int64), ("wait_flags", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
@@ -164,6 +188,9 @@ def _bind_optional(lib):
     lib.spatten_decode_quant_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     lib.spatten_decode_attn_quant.argtypes = [C.POINTER(QuantDecodeArgs), C.c_void_p]
     lib.spatten_head_select.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.spatten_decode_step_workspace_bytes.restype = C.c_size_t
+    lib.spatten_decode_step_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    lib.spatten_decode_step.argtypes = [C.POINTER(StepArgs), C.c_void_p]
 
 
 def check(code: int):

@@ -104,4 +104,21 @@ struct VecT<8> {
   using type = uint2;
 };
 
+constexpr float kLog2e = 1.4426950408889634f;
+
+template <int N>
+struct HalfVec {
+  __half2 h[N];
+};
+
+// x / c with the result of an IEEE fp32 division (what torch's fp16 `tensor / sqrt(D)` computes in its fp32
+// opmath, modify_llama.py:111-113) for finite x: one Markstein correction of x * RN(1/c).  Falls back to the
+// uncorrected product when the correction is not finite (x = +-inf).
+__device__ __forceinline__ float div_by_const(float x, float c, float rc) {
+  const float y = x * rc;
+  const float r = fmaf(-y, c, x);
+  const float y2 = fmaf(r, rc, y);
+  return (fabsf(y2) <= 3.4028234e38f) ? y2 : y;
+}
+
 }  // namespace spatten

@@ -47,7 +47,6 @@ constexpr int kMaxSplits = 256;     // splits per row the merge handles
 constexpr int kMaxPeers = 8;        // GPUs of one NVSwitch domain that can receive the fused output exchange
 constexpr int kMaxClusterSize = 8;  // CTAs per cluster in cluster mode: 8 (portable maximum) or 4
 constexpr size_t kTicketBytes = static_cast<size_t>(kMaxPartials) * sizeof(unsigned int);  // per-row tickets
-constexpr float kLog2e = 1.4426950408889634f;
 
 struct DecodeParams {
   const __half* q;
@@ -144,21 +143,6 @@ __device__ __forceinline__ void signal_peers(const DecodeParams& p, int lane) {
   }
 }
 
-template <int N>
-struct HalfVec {
-  __half2 h[N];
-};
-
-// x / c with the result of an IEEE fp32 division (what torch's fp16 `tensor / sqrt(D)` computes in its fp32
-// opmath, modify_llama.py:111-113) for finite x: one Markstein correction of x * RN(1/c).  Falls back to the
-// uncorrected product when the correction is not finite (x = +-inf).
-__device__ __forceinline__ float div_by_const(float x, float c, float rc) {
-  const float y = x * rc;
-  const float r = fmaf(-y, c, x);
-  const float y2 = fmaf(r, rc, y);
-  return (fabsf(y2) <= 3.4028234e38f) ? y2 : y;
-}
-
 template <int D, int MODE, bool DBG, int kPasses>   // MODE 0: global partials + tickets (or one split); MODE 1: cluster / DSMEM merge
 __global__ void __launch_bounds__(kThreads, kPasses == 2 ? 2 : 1) decode_attn_kernel(const DecodeParams p) {
   constexpr int kTile = 4 * kPasses;  // tokens per pipeline stage (per warp)
@@ -211,6 +195,27 @@ __global__ void __launch_bounds__(kThreads, kPasses == 2 ? 2 : 1) decode_attn_ke
   if (!live || t0 >= t1c) { t0 = 0; t1c = 0; }
   const int last_split = p.kv_len > 0 ? (p.kv_len - 1) / p.tok_per_split : 0;
   const bool owns_new = live && p.append && split == last_split;   // token index kv_len (== t1c) is ours
+  // Who stores the appended K/V row of a kv head into the cache (modify_llama.py:95-100)?  The first LIVE query head of
+  // the GQA group -- and when head pruning has switched the whole group off, the warp that owns the dead row of the
+  // group's first head copies it straight from k_new/v_new, so later steps never find a hole in the cache.
+  bool new_writer = (h % p.n_rep) == 0;
+  if (p.head_mask != nullptr && row_ok && p.append && split == last_split) {
+    int first_live = -1;
+    for (int r = p.n_rep - 1; r >= 0; --r)
+      if (p.head_mask[kvh * p.n_rep + r] != 0) first_live = kvh * p.n_rep + r;
+    new_writer = h == first_live;
+    if (!live && first_live < 0 && (h % p.n_rep) == 0) {
+      constexpr int kChunksA = D * 2 / 16;
+#pragma unroll 1
+      for (int w = lane / kChunksA; w < 2; w += 32 / kChunksA) {
+        const int ch = lane % kChunksA;
+        const __half* src = (w ? p.v_new : p.k_new) + (static_cast<int64_t>(bi) * p.H_kv + kvh) * D + ch * 8;
+        __half* dst = (w ? p.v_cache : p.k_cache) + bi * p.stride_b + kvh * p.stride_h +
+                      static_cast<int64_t>(p.kv_len) * D + ch * 8;
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+      }
+    }
+  }
   if (owns_new && t1c == 0) t0 = p.kv_len;                         // kv_len == 0: the range is just the new token
   const int t_end = owns_new ? p.kv_len + 1 : t1c;
   const int nt = t_end > t0 ? (t_end - t0 + kTile - 1) / kTile : 0;
@@ -343,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, kPasses == 2 ? 2 : 1) decode_attn_ke
         const __half* src = (w ? p.v_new : p.k_new) + (static_cast<int64_t>(bi) * p.H_kv + kvh) * D + ch * 8;
         const uint4 val = *reinterpret_cast<const uint4*>(src);
         *reinterpret_cast<uint4*>((w ? Vs : Ks) + r * kRowBytes + ch * 16) = val;
-        if ((h % p.n_rep) == 0) {                        // one writer per kv head
+        if (new_writer) {                                // one writer per kv head
           __half* dst = (w ? p.v_cache : p.k_cache) + bi * p.stride_b + kvh * p.stride_h +
                         static_cast<int64_t>(p.kv_len) * D + ch * 8;
           *reinterpret_cast<uint4*>(dst) = val;

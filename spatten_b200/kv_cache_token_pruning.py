@@ -13,6 +13,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
+from .cache_buffer import CacheBuffer
 
 
 class SpAttenKVCache:
@@ -53,5 +54,6 @@ class SpAttenKVCache:
             self.keep_indices.append(keep)
             # room for the tokens the caller announced plus some slack, so decode appends in place
             k2, v2 = ops.kv_gather(k, v, keep, capacity=keep_total + int(num_coming) + 64)
-            out.append([k2, v2])
+            # fresh buffers of ours: the patched forward may append behind these views in place
+            out.append([CacheBuffer(k2._base, keep_total).view(keep_total), CacheBuffer(v2._base, keep_total).view(keep_total)])
         return out

@@ -99,6 +99,8 @@ def make_decode_args(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tens
             raise ValueError("mask must be contiguous fp16 [b, q_len, kv_len+append]")
         a.mask = mask.data_ptr()
     if head_mask is not None:
+        if head_mask.dtype != torch.uint8 or head_mask.numel() != H or not head_mask.is_contiguous():
+            raise ValueError("head_mask must be contiguous uint8 [H] (the kernel reads one byte per head)")
         a.head_mask = head_mask.data_ptr()
     a.out = out.data_ptr() if out is not None else None
     if logits is not None:
@@ -108,8 +110,17 @@ def make_decode_args(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tens
         if q_len > 1:
             a.logits_stride_q = logits.stride(2)
     if importance is not None:
+        if (importance.dtype != torch.float32 or importance.dim() != 3 or importance.shape[:2] != (b, H)
+                or importance.shape[2] < n_total or importance.stride(2) != 1
+                or importance.stride(0) != H * importance.stride(1)):
+            raise ValueError("importance must be fp32 [b, H, >= kv_len+append] with contiguous tokens and (b, H) rows "
+                             "one stride apart (the kernel indexes row * stride)")
+        if logits is None:
+            raise ValueError("importance needs a logits buffer (probabilities are recomputed from the exported logits)")
         a.importance, a.importance_stride = importance.data_ptr(), importance.stride(1)
     if head_importance is not None:
+        if head_importance.dtype != torch.float32 or head_importance.numel() != H or not head_importance.is_contiguous():
+            raise ValueError("head_importance must be contiguous fp32 [H]")
         a.head_importance = head_importance.data_ptr()
     ws = decode_workspace(q.device, b * q_len, H, D)
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
@@ -133,6 +144,96 @@ def decode_attn(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, k
     with torch.cuda.device(q.device):
         _lib.check(_lib.load().spatten_decode_attn(C.byref(a), C.c_void_p(_stream_ptr(q.device))))
     return out
+
+
+class DecodeStep:
+    """One decode token through the attention core of EVERY layer in one persistent launch -- `spatten_decode_step`.
+
+    q / k_new / v_new: fp16 [L, b, H(_kv), D]; k_caches / v_caches: per-layer fp16 [b, H_kv, cap, D] (equal strides);
+    out fp16 [L, b, H, D]; logits optional fp16 [L, b, H, >= kv_len+append]; importance optional fp32 like logits;
+    head_mask optional u8 [L, H]; head_importance optional fp32 [H].  `chain=True` keeps the decoder's ordering:
+    layer l+1's query is read only after every row of layer l has been stored.  The struct is built once;
+    `launch()` enqueues the step on the current (or given) stream and is CUDA-graph capturable.
+    """
+
+    def __init__(self, q, k_caches, v_caches, kv_len: int, rope, k_new=None, v_new=None, q_pos=None, out=None,
+                 logits=None, importance=None, head_mask=None, head_importance=None, chain: bool = True):
+        lib = _lib.load()
+        _require_cuda(q, rope, k_new, v_new, q_pos, out, logits, importance, head_mask, head_importance, *k_caches, *v_caches)
+        L, b, H, D = q.shape
+        H_kv = k_caches[0].shape[1]
+        if len(k_caches) != L or len(v_caches) != L:
+            raise ValueError("DecodeStep: one K and one V cache per layer")
+        if q.dtype != torch.float16 or not q.is_contiguous():
+            raise TypeError("DecodeStep: q must be contiguous fp16 [L, b, H, D]")
+        st = k_caches[0].stride()
+        for t in list(k_caches) + list(v_caches):
+            if t.dtype != torch.float16 or t.stride() != st or t.stride(3) != 1 or t.stride(2) != D or t.shape[1] != H_kv:
+                raise ValueError("DecodeStep: caches must be fp16 [b, H_kv, cap, D] with contiguous rows and equal strides")
+        append = k_new is not None
+        if append and not (k_new.is_contiguous() and v_new.is_contiguous() and k_new.shape == (L, b, H_kv, D)
+                           and v_new.shape == k_new.shape and k_new.dtype == torch.float16 and v_new.dtype == torch.float16):
+            raise ValueError("DecodeStep: k_new / v_new must be contiguous fp16 [L, b, H_kv, D]")
+        n_total = int(kv_len) + int(append)
+        dev = q.device
+        if out is None:
+            out = torch.empty((L, b, H, D), dtype=torch.float16, device=dev)
+        elif out.shape != q.shape or not out.is_contiguous() or out.dtype != torch.float16:
+            raise ValueError("DecodeStep: out must be contiguous fp16 [L, b, H, D]")
+        for name, t, dt in (("logits", logits, torch.float16), ("importance", importance, torch.float32)):
+            if t is not None and (t.dtype != dt or t.dim() != 4 or t.shape[:3] != (L, b, H) or t.stride(3) != 1
+                                  or t.shape[3] < n_total or t.stride(1) != H * t.stride(2)):
+                raise ValueError(f"DecodeStep: {name} must be {dt} [L, b, H, >= kv_len+append], heads x tokens contiguous")
+        if importance is not None and logits is None:
+            raise ValueError("DecodeStep: importance needs logits")
+        if head_mask is not None and (head_mask.dtype != torch.uint8 or head_mask.shape != (L, H) or not head_mask.is_contiguous()):
+            raise ValueError("DecodeStep: head_mask must be contiguous uint8 [L, H]")
+        if head_importance is not None and (head_importance.dtype != torch.float32 or head_importance.numel() != H
+                                            or not head_importance.is_contiguous()):
+            raise ValueError("DecodeStep: head_importance must be contiguous fp32 [H]")
+        if q_pos is not None and (q_pos.dtype != torch.int64 or q_pos.numel() != b or not q_pos.is_contiguous()):
+            raise TypeError("DecodeStep: q_pos must be contiguous int64 [b]")
+        table = torch.zeros((L, 8), dtype=torch.int64)
+        for l in range(L):
+            table[l, 0] = q[l].data_ptr()
+            table[l, 1] = k_new[l].data_ptr() if append else 0
+            table[l, 2] = v_new[l].data_ptr() if append else 0
+            table[l, 3], table[l, 4] = k_caches[l].data_ptr(), v_caches[l].data_ptr()
+            table[l, 5] = out[l].data_ptr()
+            table[l, 6] = logits[l].data_ptr() if logits is not None else 0
+            table[l, 7] = importance[l].data_ptr() if importance is not None else 0
+        self.table = table.to(dev)
+        need = lib.spatten_decode_step_workspace_bytes(L, b, H, D)
+        self.workspace = torch.zeros(need, dtype=torch.uint8, device=dev)
+        a = _lib.StepArgs()
+        a.struct_size = C.sizeof(_lib.StepArgs)
+        a.num_layers, a.batch, a.num_heads, a.num_kv_heads, a.head_dim = L, b, H, H_kv, D
+        a.kv_len, a.rope_len, a.append = int(kv_len), rope.shape[0], int(append)
+        a.flags = _lib.STEP_CHAIN if chain else 0
+        a.layers = self.table.data_ptr()
+        a.cache_stride_b, a.cache_stride_h = st[0], st[1]
+        a.logits_stride = logits.stride(2) if logits is not None else 0
+        a.importance_stride = importance.stride(2) if importance is not None else 0
+        a.rope = rope.data_ptr()
+        a.q_pos = q_pos.data_ptr() if q_pos is not None else None
+        a.head_mask = head_mask.data_ptr() if head_mask is not None else None
+        a.head_importance = head_importance.data_ptr() if head_importance is not None else None
+        a.workspace, a.workspace_bytes = self.workspace.data_ptr(), self.workspace.numel()
+        self.args, self.out, self.device = a, out, dev
+        self._keep = (q, k_new, v_new, list(k_caches), list(v_caches), rope, q_pos, logits, importance, head_mask,
+                      head_importance)
+
+    def launch(self, stream_ptr: Optional[int] = None):
+        sp = _stream_ptr(self.device) if stream_ptr is None else stream_ptr
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().spatten_decode_step(C.byref(self.args), C.c_void_p(sp)))
+        return self.out
+
+    def steps_completed(self) -> int:
+        return int(self.workspace[:4].view(torch.int32).item())
+
+    def timed_out(self) -> bool:
+        return bool(self.workspace[8:12].view(torch.int32).item())
 
 
 def prefill_attn(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, kv_len: int, rope: torch.Tensor,

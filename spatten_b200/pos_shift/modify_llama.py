@@ -20,37 +20,23 @@ import torch
 import torch.nn.functional as F
 
 from .. import _lib, ops
+from ..cache_buffer import CacheBuffer
 
 __all__ = ["enable_llama_pos_shift_attention", "llama_pos_shift_attention_forward"]
 
 _GROW = 256           # minimum spare rows when a cache buffer has to be (re)allocated
 
 
-def _capacity_view(t: torch.Tensor, D: int):
-    """If `t` [b,H,S,D] is a window onto a larger per-head buffer, return (full-capacity view, capacity)."""
-    b, H, S, _ = t.shape
-    if t.stride(3) != 1 or t.stride(2) != D or (b > 1 and t.stride(0) < H * t.stride(1)):
-        return None, 0
-    cap = t.stride(1) // D if H > 1 else (t.stride(0) // D if b > 1 else S)
-    if H == 1 and b == 1:
-        cap = (t.untyped_storage().nbytes() // t.element_size() - t.storage_offset()) // D
-    last = t.storage_offset() + (b - 1) * t.stride(0) + (H - 1) * t.stride(1) + cap * D
-    if cap < S or last * t.element_size() > t.untyped_storage().nbytes():
-        return None, 0
-    return t.as_strided((b, H, cap, D), t.stride(), t.storage_offset()), cap
-
-
-def _grow(past: Optional[torch.Tensor], b, H_kv, D, have, need, device):
-    """Buffer [b,H_kv,cap,D] holding the first `have` rows of `past`, cap >= need (amortised doubling)."""
-    if past is not None:
-        full, cap = _capacity_view(past, D)
-        if full is not None and cap >= need:
-            return full
+def _grow(past: Optional[torch.Tensor], b, H_kv, D, have, need, device) -> CacheBuffer:
+    """CacheBuffer holding the first `have` rows of `past` with capacity >= need (amortised doubling)."""
+    cb = CacheBuffer.of(past)
+    if cb is not None and cb.buf.shape[2] >= need and cb.buf.shape[:2] == (b, H_kv) and cb.buf.device == device:
+        return cb
     cap = max(need + _GROW, 2 * have)
     buf = torch.empty((b, H_kv, cap, D), dtype=torch.float16, device=device)
     if past is not None and have:
         buf[:, :, :have].copy_(past)
-    return buf
+    return CacheBuffer(buf, have)
 
 
 def _rope_for(self, device, need: int) -> torch.Tensor:
@@ -91,7 +77,10 @@ def llama_pos_shift_attention_forward(
     past_len = past_key_value[0].shape[-2] if past_key_value is not None else 0
     kv_seq_len = past_len + q_len                                                    # :86-88
     if position_ids is None:
-        position_ids = torch.arange(past_len, kv_seq_len, device=dev).unsqueeze(0).expand(bsz, q_len)
+        position_ids = torch.arange(past_len, kv_seq_len, device=dev).unsqueeze(0)
+    # transformers-4.33 LlamaModel builds default position_ids of shape [1, q_len]; the reference broadcasts them
+    # through cos[position_ids] (:23-26)
+    position_ids = position_ids.to(torch.int64).expand(bsz, q_len).contiguous()
     rope = _rope_for(self, dev, kv_seq_len)
 
     mask = None
@@ -103,12 +92,13 @@ def llama_pos_shift_attention_forward(
 
     past_k = past_key_value[0] if past_key_value is not None else None
     past_v = past_key_value[1] if past_key_value is not None else None
-    kbuf = _grow(past_k, bsz, H_kv, D, past_len, kv_seq_len, dev)
-    vbuf = _grow(past_v, bsz, H_kv, D, past_len, kv_seq_len, dev)
-    if vbuf.stride() != kbuf.stride():                     # keep K and V congruent for the kernel
-        vbuf2 = torch.empty_strided(kbuf.shape, kbuf.stride(), dtype=torch.float16, device=dev)
-        vbuf2[:, :, :past_len].copy_(vbuf[:, :, :past_len])
-        vbuf = vbuf2
+    kcb = _grow(past_k, bsz, H_kv, D, past_len, kv_seq_len, dev)
+    vcb = _grow(past_v, bsz, H_kv, D, past_len, kv_seq_len, dev)
+    if vcb.buf.stride() != kcb.buf.stride():               # keep K and V congruent for the kernel
+        vb2 = torch.empty_strided(kcb.buf.shape, kcb.buf.stride(), dtype=torch.float16, device=dev)
+        vb2[:, :, :past_len].copy_(vcb.buf[:, :, :past_len])
+        vcb = CacheBuffer(vb2, past_len)
+    kbuf, vbuf = kcb.buf, vcb.buf
 
     if q_len == 1:
         scores = torch.empty((bsz, H, 1, kv_seq_len), dtype=torch.float16, device=dev)
@@ -138,7 +128,8 @@ def llama_pos_shift_attention_forward(
     if output_attentions:                                                            # :135-137, :165-166
         s = scores if attention_mask is None else scores + attention_mask.to(torch.float16)
         attn_weights = F.softmax(s, dim=-1, dtype=torch.float32).to(torch.float16)
-    present = (kbuf[:, :, :kv_seq_len], vbuf[:, :, :kv_seq_len]) if use_cache else None   # :100
+    # the rows are in the buffers either way; without use_cache the views are simply not handed out
+    present = (kcb.view(kv_seq_len), vcb.view(kv_seq_len)) if use_cache else None        # :100
     return attn_output, attn_weights, present
 
 

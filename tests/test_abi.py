@@ -33,7 +33,9 @@ def test_struct_layouts_match_c():
     #include <stdio.h>
     #include "spatten_b200.h"
     int main(void) {
-      printf("%zu %zu %zu\n", sizeof(SpattenDecodeArgs), sizeof(SpattenSelectArgs), sizeof(SpattenGatherArgs));
+      printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(SpattenDecodeArgs), sizeof(SpattenSelectArgs), sizeof(SpattenGatherArgs),
+             sizeof(SpattenStepLayer), sizeof(SpattenStepArgs), sizeof(SpattenPrefillArgs), sizeof(SpattenSparsePvArgs),
+             sizeof(SpattenQuantDecodeArgs));
       return 0;
     }'''
     with tempfile.TemporaryDirectory() as td:
@@ -41,7 +43,10 @@ def test_struct_layouts_match_c():
         open(src, "w").write(prog)
         subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
         sizes = list(map(int, subprocess.check_output([exe]).split()))
-    assert sizes == [C.sizeof(_lib.DecodeArgs), C.sizeof(_lib.SelectArgs), C.sizeof(_lib.GatherArgs)]
+    assert sizes == [C.sizeof(_lib.DecodeArgs), C.sizeof(_lib.SelectArgs), C.sizeof(_lib.GatherArgs),
+                     C.sizeof(_lib.StepLayer), C.sizeof(_lib.StepArgs), C.sizeof(_lib.PrefillArgs),
+                     C.sizeof(_lib.SparsePvArgs), C.sizeof(_lib.QuantDecodeArgs)]
+    assert C.sizeof(_lib.StepLayer) == 64
 
 
 def test_argument_validation_without_gpu():
@@ -85,13 +90,17 @@ def test_product_package_does_not_import_the_oracle():
                 assert not pat.search(src), f"{f} imports / calls the oracle"
 
 
-def test_capacity_view_logic_cpu():
+def test_cache_buffer_ownership_cpu():
+    """In-place append is allowed only behind the NEWEST view of a buffer this package allocated."""
     import torch
-    from spatten_b200.pos_shift.modify_llama import _capacity_view
+    from spatten_b200.cache_buffer import CacheBuffer
     buf = torch.zeros(2, 3, 50, 8, dtype=torch.float16)
-    full, cap = _capacity_view(buf[:, :, :20], 8)
-    assert cap == 50 and full.shape == (2, 3, 50, 8) and full.data_ptr() == buf.data_ptr()
-    plain = torch.zeros(2, 3, 20, 8, dtype=torch.float16)
-    full, cap = _capacity_view(plain, 8)
-    assert cap == 20
-    assert _capacity_view(plain.transpose(1, 2), 8) == (None, 0)
+    cb = CacheBuffer(buf, 0)
+    v20 = cb.view(20)
+    assert CacheBuffer.of(v20) is cb and v20.shape == (2, 3, 20, 8)
+    v21 = cb.view(21)
+    assert CacheBuffer.of(v21) is cb
+    assert CacheBuffer.of(v20) is None                     # stale: something was appended behind it already
+    assert CacheBuffer.of(buf[:, :, :21]) is None          # a caller's own view of the same storage
+    assert CacheBuffer.of(v21[:, :, :10]) is None and CacheBuffer.of(v21.clone()) is None
+    assert CacheBuffer.of(None) is None

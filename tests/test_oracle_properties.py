@@ -1,7 +1,10 @@
 """Property tests (hypothesis) of the oracle's selection rule and of the unpinned restatements' self-consistency."""
 import numpy as np
+import pytest
 import torch
-from hypothesis import given, settings, strategies as st
+
+pytest.importorskip("hypothesis")      # optional test dependency: skip this module instead of a collection error
+from hypothesis import given, settings, strategies as st  # noqa: E402
 
 from oracle import spatten_oracle as O
 

@@ -1,5 +1,5 @@
 """2-GPU check of the fused output exchange (in-kernel peer stores + flag wait).  Skipped on single-GPU boxes; the
-same script was run at 2 and 8 GPUs during the round (`tools/peer_test.py`)."""
+same script was run at 2 and 8 GPUs during the round (`tools/peer_check.py`)."""
 import os
 import socket
 import subprocess
@@ -21,7 +21,7 @@ def test_fused_exchange_two_gpus(fold_wait):
     s.close()
     env = dict(os.environ, FOLD_WAIT=fold_wait)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "peer_test.py")],
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "peer_check.py")],
                        env=env, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("fused exchange OK") == 2

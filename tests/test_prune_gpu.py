@@ -130,7 +130,7 @@ def test_gather_in_place_equals_out_of_place():
 def test_prune_then_decode_appends_in_place():
     """After a prune the returned views have spare capacity, so the next forward appends without realloc."""
     from spatten_b200.kv_cache_token_pruning import SpAttenKVCache
-    from spatten_b200.pos_shift.modify_llama import _capacity_view
+    from spatten_b200.cache_buffer import CacheBuffer
     H, S, D = 4, 400, 128
     k = det_normal((1, H, S, D), 81, 1.0, torch.float16).cuda()
     v = det_normal((1, H, S, D), 82, 1.0, torch.float16).cuda()
@@ -138,8 +138,8 @@ def test_prune_then_decode_appends_in_place():
     cache = SpAttenKVCache(4, 50, 50)
     (k2, v2), = cache.apply_token_pruning([(k, v)], 10, [s])
     assert k2.shape[2] == 4 + 50 + 40
-    full, cap = _capacity_view(k2, D)
-    assert full is not None and cap >= k2.shape[2] + 10
+    cb = CacheBuffer.of(k2)
+    assert cb is not None and cb.buf.shape[2] >= k2.shape[2] + 10 and CacheBuffer.of(v2) is not None
 
 
 def test_prune_error_behaviour_matches_reference():

@@ -56,6 +56,26 @@ def bench_shape(b, H, D, n, L, iters, logits_on=True, graph=True, flags=0):
             "frac_6445": round(bytes_layer / us_layer / 1e3 / 6445, 4)}
 
 
+def bench_step(b, H, D, n, L, iters, chain=True, logits_on=True):
+    """The persistent decode-step kernel: ONE launch for all L layers (spatten_decode_step)."""
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(1)
+    kc = [torch.randn((b, H, n + 8, D), generator=g, device=dev, dtype=torch.float16) for _ in range(L)]
+    vc = [torch.randn((b, H, n + 8, D), generator=g, device=dev, dtype=torch.float16) for _ in range(L)]
+    q = torch.randn((L, b, H, D), generator=g, device=dev, dtype=torch.float16)
+    kn = torch.randn((L, b, H, D), generator=g, device=dev, dtype=torch.float16)
+    vn = torch.randn((L, b, H, D), generator=g, device=dev, dtype=torch.float16)
+    rope = ops.rope_table(D, n + 8, dev)
+    logits = torch.empty((L, b, H, n + 8), device=dev, dtype=torch.float16) if logits_on else None
+    step = ops.DecodeStep(q, kc, vc, n - 1, rope, k_new=kn, v_new=vn, logits=logits, chain=chain)
+    ms = _time_graph(step.launch, iters)
+    bytes_layer = 2 * b * H * n * D * 2
+    us_layer = ms * 1e3 / L
+    return {"kind": "decode_step", "b": b, "H": H, "D": D, "n": n, "L": L, "chain": chain, "logits": logits_on,
+            "us_per_layer": round(us_layer, 3), "GBps": round(bytes_layer / us_layer / 1e3, 1),
+            "frac_6445": round(bytes_layer / us_layer / 1e3 / 6445, 4), "timed_out": step.timed_out()}
+
+
 def _time_graph(fn, iters):
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
@@ -200,7 +220,19 @@ if __name__ == "__main__":
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--extra", action="store_true", help="config-4 quantised decode and Mode-B local-V timings")
     ap.add_argument("--prefill", action="store_true", help="tcgen05 prefill attention timings")
+    ap.add_argument("--step", action="store_true", help="persistent decode-step kernel timings")
+    ap.add_argument("--no-chain", action="store_true")
     a = ap.parse_args()
+    if a.step:
+        if a.shape:
+            shapes = [tuple(map(int, a.shape.split(",")))]
+        else:
+            shapes = [(1, 32, 128, 2048, 32), (1, 32, 128, 4096, 32), (1, 32, 128, 8192, 16), (8, 5, 128, 16384, 8),
+                      (1, 24, 128, 4096, 32), (1, 4, 128, 2048, 32), (1, 32, 128, 512, 32), (1, 40, 128, 2048, 40)]
+        for (b, H, D, n, L) in shapes:
+            for chain in ((False,) if a.no_chain else (True, False)):
+                print(json.dumps(bench_step(b, H, D, n, L, a.iters, chain=chain)), flush=True)
+        sys.exit(0)
     if a.extra:
         bench_extra(a.iters)
         sys.exit(0)
