@@ -26,17 +26,13 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "../../include/spatten_b200.h"
 #include "common.cuh"
 
 namespace spatten {
 
-constexpr int kStepWarps = 8;
-constexpr int kStepThreads = kStepWarps * 32;
-constexpr int kStepStages = 3;
-constexpr int kStepTile = 16;        // tokens per stage: 4 passes of 4 keys x 8 lanes
-constexpr int kStepPasses = 4;
 constexpr int kStepMaxPeers = 8;
 constexpr int kStepRot = 1;          // work-range rotation per layer (warps)
 constexpr int kStepCtrlWords = 64;   // workspace header: [0] steps completed, [1] exit ticket, [2] wait timed out
@@ -72,12 +68,15 @@ struct StepParams {
   float sqrt_d, rsqrt_d;
 };
 
+// Work-list cursor.  Every lane keeps the same copy; set_layer() ballots, so it is called warp-uniformly.
 struct Cursor {
   int l;                   // layer (>= L: exhausted)
   int t, t_end;            // this warp's tile range in the layer's live tile list
-  int i, j;                // live row index, tile inside the row
-  int nlh;                 // live heads of the layer
+  int j;                   // tile inside the current row
+  int i;                   // live row index
+  int bi, h;               // sequence and head of the current row
   int first;               // 1 until the first tile of the range has been passed
+  int nlh;                 // live heads of the layer
   unsigned long long hm;   // live head bits of the layer (valid when head_mask != nullptr)
 };
 
@@ -95,8 +94,23 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* ptr, int sys) {
   return v;
 }
 
-template <int D>
-__global__ void __launch_bounds__(kStepThreads, 1) decode_step_kernel(const StepParams p) {
+// arm the stage's mbarrier and start the K and V bulk copies -- executed by the lane for which `pred` is set, without
+// a divergent branch
+__device__ __forceinline__ void issue_kv_copies(bool pred, uint32_t k_dst, uint32_t v_dst, const void* k_src, const void* v_src,
+                                                uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t"
+      "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %2;\n\t"
+      "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%3], [%4], %5, [%1], %6;\n\t"
+      "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%7], [%8], %5, [%1], %6;\n\t}"
+      ::"r"(static_cast<uint32_t>(pred)), "r"(bar), "r"(2 * bytes), "r"(k_dst), "l"(k_src), "r"(bytes), "l"(policy), "r"(v_dst),
+        "l"(v_src)
+      : "memory");
+}
+
+template <int D, int WARPS, int STAGES, int PASSES>
+__global__ void __launch_bounds__(WARPS * 32, 1) decode_step_kernel(const StepParams p) {
+  constexpr int kTile = 4 * PASSES;   // tokens per stage: PASSES passes of 4 keys x 8 lanes
   constexpr int E2 = D / 16;   // halves per lane in each half of the row (8 lanes cover D/2)
   constexpr int NH2 = E2 / 2;  // half2 per lane per half-row
   constexpr int VB = E2 * 2;   // bytes per lane per half-row
@@ -105,22 +119,25 @@ __global__ void __launch_bounds__(kStepThreads, 1) decode_step_kernel(const Step
   using HV = HalfVec<NH2>;
   using PV_t = typename VecT<PER * 4>::type;
   constexpr int kRowBytes = D * 2;
-  constexpr int kTileBytes = kStepTile * kRowBytes;
-  constexpr int kWarpSmem = kStepStages * 2 * kTileBytes;
+  constexpr int kTileBytes = kTile * kRowBytes;
+  constexpr int kStageBytes = 2 * kTileBytes;
+  constexpr int kWarpSmem = STAGES * kStageBytes;
 
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 3, c = lane & 7;
   uint8_t* wsm = smem + warp * kWarpSmem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStepWarps * kWarpSmem) + warp * kStepStages;
-  const int gw = blockIdx.x * kStepWarps + warp;
+  const uint32_t wsm_u32 = smem_u32(wsm);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WARPS * kWarpSmem) + warp * STAGES;
+  const uint32_t bars_u32 = smem_u32(bars);
+  const int gw = blockIdx.x * WARPS + warp;
 
-  // layer descriptors: 64 bytes each, read at every segment start / issue -- keep them on chip
+  // layer descriptors: 64 bytes each, read at every segment start / row change -- keep them on chip
   const SpattenStepLayer* lys = p.layers;
   if (p.L <= kStepSmemLayers) {
-    uint4* dst = reinterpret_cast<uint4*>(smem + kStepWarps * kWarpSmem + kStepWarps * kStepStages * 8);
+    uint4* dst = reinterpret_cast<uint4*>(smem + WARPS * kWarpSmem + WARPS * STAGES * 8);
     const uint4* src = reinterpret_cast<const uint4*>(p.layers);
-    for (int k = threadIdx.x; k < p.L * 4; k += kStepThreads) dst[k] = src[k];
+    for (int k = threadIdx.x; k < p.L * 4; k += WARPS * 32) dst[k] = src[k];
     lys = reinterpret_cast<const SpattenStepLayer*>(dst);
     __syncthreads();
   }
@@ -128,9 +145,14 @@ __global__ void __launch_bounds__(kStepThreads, 1) decode_step_kernel(const Step
   const unsigned epoch = *reinterpret_cast<volatile const unsigned*>(p.ctrl);
   const unsigned flag_target = (epoch + 1u) * p.rows;
 
-  // ---- work-list cursors (every lane keeps the same copy; ballots inside => call warp-uniformly) -------------
+  // ---- cursors ------------------------------------------------------------------------------------------------
+  auto set_row = [&](Cursor& cu) {                       // (bi, h) of live row cu.i
+    cu.bi = cu.i / cu.nlh;
+    const int hidx = cu.i - cu.bi * cu.nlh;
+    cu.h = p.head_mask ? nth_set_bit64(cu.hm, hidx) : hidx;
+  };
   auto set_layer = [&](Cursor& cu, int l) {
-    cu.l = l; cu.t = 0; cu.t_end = 0; cu.i = 0; cu.j = 0; cu.first = 1; cu.nlh = p.H; cu.hm = ~0ull;
+    cu.l = l; cu.t = 0; cu.t_end = 0; cu.i = 0; cu.j = 0; cu.first = 1; cu.nlh = p.H; cu.hm = ~0ull; cu.bi = 0; cu.h = 0;
     if (l >= p.L) return;
     if (p.head_mask) {
       const uint8_t* hr = p.head_mask + static_cast<size_t>(l) * p.H;
@@ -139,58 +161,68 @@ __global__ void __launch_bounds__(kStepThreads, 1) decode_step_kernel(const Step
       cu.hm = static_cast<unsigned long long>(lo) | (static_cast<unsigned long long>(hi) << 32);
       cu.nlh = __popcll(cu.hm);
     }
-    const long long T = static_cast<long long>(p.b) * cu.nlh * p.tpr;
-    const long long weff = T < p.W ? T : p.W;
-    const int v = (gw + l * kStepRot) % p.W;
+    const unsigned T = static_cast<unsigned>(p.b * cu.nlh * p.tpr);   // host checked: T * W < 2^32
+    const unsigned weff = T < static_cast<unsigned>(p.W) ? T : static_cast<unsigned>(p.W);
+    const unsigned v = static_cast<unsigned>(gw + l * kStepRot) % static_cast<unsigned>(p.W);
     if (v < weff) {
       cu.t = static_cast<int>(v * T / weff);
       cu.t_end = static_cast<int>((v + 1) * T / weff);
       cu.i = cu.t / p.tpr;
       cu.j = cu.t - cu.i * p.tpr;
+      set_row(cu);
     }
   };
-  auto seek = [&](Cursor& cu) {
-    while (cu.l < p.L && cu.t >= cu.t_end) set_layer(cu, cu.l + 1);
-  };
-  auto advance = [&](Cursor& cu) {
-    cu.first = 0;
-    ++cu.t;
-    if (++cu.j == p.tpr) { cu.j = 0; ++cu.i; }
-    if (cu.t >= cu.t_end) { set_layer(cu, cu.l + 1); seek(cu); }
-  };
-  auto row_of = [&](const Cursor& cu, int& bi, int& h) {
-    bi = cu.i / cu.nlh;
-    const int hidx = cu.i - bi * cu.nlh;
-    h = p.head_mask ? nth_set_bit64(cu.hm, hidx) : hidx;
+  // slow path of advance(): the row or the range ended
+  auto advance_slow = [&](Cursor& cu) {
+    if (cu.t >= cu.t_end) {
+      do set_layer(cu, cu.l + 1); while (cu.l < p.L && cu.t >= cu.t_end);
+    } else {
+      cu.j = 0;
+      ++cu.i;
+      set_row(cu);
+    }
   };
 
   const uint64_t pol = policy_evict_first();
-  auto issue = [&](const Cursor& cu, int s) {
-    const int tok0 = cu.j * kStepTile;
-    const int ncopy = min(kStepTile, p.kv_len - tok0);        // rows that come from the cache
-    if (ncopy <= 0) return;
-    int bi, h;
-    row_of(cu, bi, h);
-    if (lane == 0) {
-      const SpattenStepLayer* ly = lys + cu.l;
-      const int64_t off = bi * p.stride_b + (h / p.n_rep) * p.stride_h + static_cast<int64_t>(tok0) * D;
-      const __half* Kc = static_cast<const __half*>(ly->k_cache) + off;
-      const __half* Vc = static_cast<const __half*>(ly->v_cache) + off;
-      const uint32_t bytes = static_cast<uint32_t>(ncopy) * kRowBytes;
-      mbar_expect_tx(&bars[s], 2 * bytes);
-      bulk_g2s(wsm + s * 2 * kTileBytes, Kc, bytes, &bars[s], pol);
-      bulk_g2s(wsm + s * 2 * kTileBytes + kTileBytes, Vc, bytes, &bars[s], pol);
-    }
+  // issue cursor: addresses of the tile it names
+  Cursor ci;
+  const __half* ik = nullptr;
+  const __half* iv = nullptr;
+  auto issue_ptrs = [&]() {
+    if (ci.l >= p.L) return;
+    const SpattenStepLayer* ly = lys + ci.l;
+    const int64_t off = ci.bi * p.stride_b + (ci.h / p.n_rep) * p.stride_h + static_cast<int64_t>(ci.j) * (kTile * D);
+    ik = static_cast<const __half*>(ly->k_cache) + off;
+    iv = static_cast<const __half*>(ly->v_cache) + off;
+  };
+  auto issue_next = [&](int s) {                          // copy the issue cursor's tile into stage s, move it on
+    if (ci.l >= p.L) return;
+    const int ncopy = min(kTile, p.kv_len - ci.j * kTile);
+    if (ncopy > 0)
+      issue_kv_copies(lane == 0, wsm_u32 + s * kStageBytes, wsm_u32 + s * kStageBytes + kTileBytes, ik, iv,
+                      static_cast<uint32_t>(ncopy) * kRowBytes, bars_u32 + s * 8, pol);
+    ++ci.t; ++ci.j;
+    ik += kTile * D; iv += kTile * D;
+    if (ci.j == p.tpr || ci.t >= ci.t_end) { advance_slow(ci); issue_ptrs(); }
   };
 
-  // RoPE rows of one tile: cos | sin for the 4 passes of this lane's key group (L1/L2 resident table)
-  auto load_table = [&](int tok0, HV (&cs)[kStepPasses], HV (&sn)[kStepPasses]) {
+  // RoPE rows of one tile: cos | sin for the 4 passes of this lane's key group (L2 resident table)
+  auto load_table = [&](int tok0, HV (&cs)[PASSES], HV (&sn)[PASSES]) {
+    if (tok0 + kTile <= p.rope_len) {
+      const __half* r = p.rope + static_cast<int64_t>(tok0 + g) * D + c * E2;
 #pragma unroll
-    for (int ps = 0; ps < kStepPasses; ++ps) {
-      const int j = min(tok0 + ps * 4 + g, p.rope_len - 1);
-      const __half* r = p.rope + static_cast<int64_t>(j) * D + c * E2;
-      *reinterpret_cast<Vec*>(&cs[ps]) = __ldg(reinterpret_cast<const Vec*>(r));
-      *reinterpret_cast<Vec*>(&sn[ps]) = __ldg(reinterpret_cast<const Vec*>(r + D / 2));
+      for (int ps = 0; ps < PASSES; ++ps) {
+        *reinterpret_cast<Vec*>(&cs[ps]) = __ldg(reinterpret_cast<const Vec*>(r + ps * 4 * D));
+        *reinterpret_cast<Vec*>(&sn[ps]) = __ldg(reinterpret_cast<const Vec*>(r + ps * 4 * D + D / 2));
+      }
+    } else {
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) {
+        const int j = min(tok0 + ps * 4 + g, p.rope_len - 1);
+        const __half* r = p.rope + static_cast<int64_t>(j) * D + c * E2;
+        *reinterpret_cast<Vec*>(&cs[ps]) = __ldg(reinterpret_cast<const Vec*>(r));
+        *reinterpret_cast<Vec*>(&sn[ps]) = __ldg(reinterpret_cast<const Vec*>(r + D / 2));
+      }
     }
   };
 
@@ -205,7 +237,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) decode_step_kernel(const Step
     __syncwarp();
   };
 
-  // every lane stored its piece of row `row` of layer `layer`: publish it
+  // every lane stored its piece of a row of layer `layer`: publish it
   auto signal_row = [&](int layer) {
     if (p.n_flag == 0) return;
     __syncwarp();
@@ -217,7 +249,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) decode_step_kernel(const Step
   };
 
   // lane owns dims [d0, d0 + PER) of the finished row: normalise, round, store (locally or to every peer), side outputs
-  auto emit_row = [&](int layer, int row, int bi, int h, int d0, const float (&o)[PER], float inv, float M) {
+  auto emit_row = [&](int layer, int row, int d0, const float (&o)[PER], float inv, float M) {
     __half oh16[PER];
     float habs = 0.f;
 #pragma unroll
@@ -240,13 +272,13 @@ __global__ void __launch_bounds__(kStepThreads, 1) decode_step_kernel(const Step
     }
     if (p.head_importance) {
       habs = warp_sum(habs);
-      if (lane == 0) atomicAdd(p.head_importance + h, habs);
+      if (lane == 0) atomicAdd(p.head_importance + row % p.H, habs);
     }
     const SpattenStepLayer* ly = lys + layer;
     if (ly->importance && ly->logits && M > -CUDART_INF_F) {
       const unsigned short* lgr = reinterpret_cast<const unsigned short*>(
-          static_cast<const __half*>(ly->logits) + (static_cast<int64_t>(bi) * p.H + h) * p.logits_stride);
-      float* imp = ly->importance + (static_cast<int64_t>(bi) * p.H + h) * p.imp_stride;
+          static_cast<const __half*>(ly->logits) + static_cast<int64_t>(row) * p.logits_stride);
+      float* imp = ly->importance + static_cast<int64_t>(row) * p.imp_stride;
 #pragma unroll 1
       for (int j = lane; j < p.n_total; j += 32) {
         const __half s16 = __ushort_as_half(__ldcg(lgr + j));
@@ -256,86 +288,91 @@ __global__ void __launch_bounds__(kStepThreads, 1) decode_step_kernel(const Step
     signal_row(layer);
   };
 
+  // pruned heads of a layer: zero their output rows, keep the KV cache complete, count them as done
+  auto dead_rows = [&](int layer, int nlh, unsigned long long hm) {
+    const SpattenStepLayer* ly = lys + layer;
+    const int ndh = p.H - nlh, n_dead = p.b * ndh;
+    const unsigned T = static_cast<unsigned>(p.b * nlh * p.tpr);
+    const int weff = static_cast<int>(T < static_cast<unsigned>(p.W) ? T : static_cast<unsigned>(p.W));
+    const int v = (gw + layer * kStepRot) % p.W;
+    const unsigned long long hall = p.H >= 64 ? ~0ull : ((1ull << p.H) - 1ull);
+#pragma unroll 1
+    for (int dr = v; dr < n_dead; dr += weff) {
+      const int dbi = dr / ndh;
+      const int dh = nth_set_bit64(~hm & hall, dr - dbi * ndh);
+      const int dkvh = dh / p.n_rep;
+      const unsigned long long grp = (hm >> (dkvh * p.n_rep)) & (p.n_rep >= 64 ? ~0ull : ((1ull << p.n_rep) - 1ull));
+      if (p.append && grp == 0 && dh == dkvh * p.n_rep) {
+        constexpr int kChunks = kRowBytes / 16;
+        const int which = lane / kChunks, ch = lane % kChunks;
+#pragma unroll 1
+        for (int w = which; w < 2; w += 32 / kChunks) {
+          const __half* src = static_cast<const __half*>(w ? ly->v_new : ly->k_new) +
+                              (static_cast<int64_t>(dbi) * p.H_kv + dkvh) * D + ch * 8;
+          __half* dst = static_cast<__half*>(w ? ly->v_cache : ly->k_cache) + dbi * p.stride_b + dkvh * p.stride_h +
+                        static_cast<int64_t>(p.kv_len) * D + ch * 8;
+          *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+        }
+      }
+      float z[PER];
+#pragma unroll
+      for (int k = 0; k < PER; ++k) z[k] = 0.f;
+      emit_row(layer, dbi * p.H + dh, lane * PER, z, 0.f, -CUDART_INF_F);
+    }
+  };
+
   // ---- pipeline prologue ----------------------------------------------------------------------------------------
   Cursor cc;
   set_layer(cc, 0);
-  seek(cc);
-  Cursor ci = cc;
+  while (cc.l < p.L && cc.t >= cc.t_end) set_layer(cc, cc.l + 1);
+  ci = cc;
+  issue_ptrs();
   if (lane == 0) {
 #pragma unroll
-    for (int s = 0; s < kStepStages; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
     fence_mbar_init();
   }
   __syncwarp();
 #pragma unroll 1
-  for (int s = 0; s < kStepStages; ++s) {
-    if (ci.l < p.L) { issue(ci, s); advance(ci); }
-  }
+  for (int s = 0; s < STAGES; ++s) issue_next(s);
 
   unsigned phase = 0;     // bit s = parity the next wait on stage s uses
   int s = 0;
   float ql[E2], qh[E2], accl[E2], acch[E2];
   float m = -CUDART_INF_F, l = 0.f;
-  HV cs[kStepPasses], sn[kStepPasses];
-  if (cc.l < p.L) load_table(cc.j * kStepTile, cs, sn);
+  HV cs[PASSES], sn[PASSES];
+  if (cc.l < p.L) load_table(cc.j * kTile, cs, sn);
+  // segment constants (a segment = this warp's tiles of one row)
+  int seg_l = 0, seg_row = 0, seg_i = 0, seg_nlh = p.H;
+  bool seg_writer = false;
+  const SpattenStepLayer* ly = lys;
+  __half* lg = nullptr;
 
 #pragma unroll 1
   while (cc.l < p.L) {
-    // ---- snapshot of the current tile, then move the cursor on (it now names the NEXT tile) -------------------
-    const int cl = cc.l, ci_row = cc.i, cj = cc.j, cnlh = cc.nlh;
-    const unsigned long long chm = cc.hm;
-    const bool first = cc.first != 0;
-    const bool seg_start = first || cj == 0;
-    const bool seg_end = (cj == p.tpr - 1) || (cc.t == cc.t_end - 1);
-    int bi, h;
-    row_of(cc, bi, h);
-    const int kvh = h / p.n_rep;
-    const int row = bi * p.H + h;
-    advance(cc);
-    HV csn[kStepPasses], snn[kStepPasses];
-    if (cc.l < p.L) load_table(cc.j * kStepTile, csn, snn);
-
-    const SpattenStepLayer* ly = lys + cl;
-    if (seg_start) {
-      if (first) {
-        // the decoder's dependency: layer cl's query exists only when every row of layer cl-1 has been stored
-        if (cl > 0 && p.chain) wait_layer(cl - 1);
-        if (p.head_mask && cnlh < p.H) {
-          // pruned heads of this layer: zero their output rows, keep the KV cache complete, count them as done
-          const int ndh = p.H - cnlh, n_dead = p.b * ndh;
-          const long long T = static_cast<long long>(p.b) * cnlh * p.tpr;
-          const int weff = static_cast<int>(T < p.W ? T : p.W);
-          const int v = (gw + cl * kStepRot) % p.W;
-          const unsigned long long hall = p.H >= 64 ? ~0ull : ((1ull << p.H) - 1ull);
-#pragma unroll 1
-          for (int dr = v; dr < n_dead; dr += weff) {
-            const int dbi = dr / ndh;
-            const int dh = nth_set_bit64(~chm & hall, dr - dbi * ndh);
-            const int dkvh = dh / p.n_rep;
-            const unsigned long long grp = (chm >> (dkvh * p.n_rep)) & (p.n_rep >= 64 ? ~0ull : ((1ull << p.n_rep) - 1ull));
-            if (p.append && grp == 0 && dh == dkvh * p.n_rep) {
-              constexpr int kChunks = kRowBytes / 16;
-              const int which = lane / kChunks, ch = lane % kChunks;
-#pragma unroll 1
-              for (int w = which; w < 2; w += 32 / kChunks) {
-                const __half* src = static_cast<const __half*>(w ? ly->v_new : ly->k_new) +
-                                    (static_cast<int64_t>(dbi) * p.H_kv + dkvh) * D + ch * 8;
-                __half* dst = static_cast<__half*>(w ? ly->v_cache : ly->k_cache) + dbi * p.stride_b + dkvh * p.stride_h +
-                              static_cast<int64_t>(p.kv_len) * D + ch * 8;
-                *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
-              }
-            }
-            float z[PER];
-#pragma unroll
-            for (int k = 0; k < PER; ++k) z[k] = 0.f;
-            emit_row(cl, dbi * p.H + dh, dbi, dh, lane * PER, z, 0.f, -CUDART_INF_F);
-          }
-        }
+    const int cj = cc.j;
+    if (cc.first | (cj == 0)) {
+      // ---- segment start ------------------------------------------------------------------------------------------
+      seg_l = cc.l; seg_i = cc.i; seg_nlh = cc.nlh;
+      const int bi = cc.bi, h = cc.h;
+      seg_row = bi * p.H + h;
+      ly = lys + seg_l;
+      if (cc.first) {
+        // the decoder's dependency: layer l's query exists only when every row of layer l-1 has been stored
+        if (seg_l > 0 && p.chain) wait_layer(seg_l - 1);
+        if (p.head_mask && seg_nlh < p.H) dead_rows(seg_l, seg_nlh, cc.hm);
       }
+      seg_writer = (h % p.n_rep) == 0;
+      if (p.head_mask) {
+        const int kvh = h / p.n_rep;
+        const unsigned long long grp = (cc.hm >> (kvh * p.n_rep)) & (p.n_rep >= 64 ? ~0ull : ((1ull << p.n_rep) - 1ull));
+        seg_writer = h == kvh * p.n_rep + (__ffsll(static_cast<long long>(grp)) - 1);   // first live head of the kv group
+      }
+      lg = ly->logits ? static_cast<__half*>(ly->logits) + static_cast<int64_t>(seg_row) * p.logits_stride : nullptr;
       // query of this row, rotated at its position id (modify_llama.py:92), fp16 op-for-op, kept as fp32
       int64_t pos = p.q_pos ? p.q_pos[bi] : p.kv_len;
       pos = max(static_cast<int64_t>(0), min(pos, static_cast<int64_t>(p.rope_len - 1)));
-      const __half* qr = static_cast<const __half*>(ly->q) + static_cast<int64_t>(row) * D;
+      const __half* qr = static_cast<const __half*>(ly->q) + static_cast<int64_t>(seg_row) * D;
       HV qa, qb, qcs, qsn;
       *reinterpret_cast<Vec*>(&qa) = *reinterpret_cast<const Vec*>(qr + c * E2);
       *reinterpret_cast<Vec*>(&qb) = *reinterpret_cast<const Vec*>(qr + D / 2 + c * E2);
@@ -354,16 +391,16 @@ __global__ void __launch_bounds__(kStepThreads, 1) decode_step_kernel(const Step
 #pragma unroll
       for (int k = 0; k < E2; ++k) accl[k] = acch[k] = 0.f;
     }
+    const bool seg_end = (cj == p.tpr - 1) | (cc.t == cc.t_end - 1);
 
-    // ---- one tile ---------------------------------------------------------------------------------------------
-    const int tok0 = cj * kStepTile;
-    const int ntok = min(kStepTile, p.n_total - tok0);           // valid tokens (incl. the appended one)
-    const int ncopy = max(0, min(kStepTile, p.kv_len - tok0));   // of which bulk-copied from the cache
-    uint8_t* Ks = wsm + s * 2 * kTileBytes;
+    // ---- one tile -------------------------------------------------------------------------------------------------
+    const int tok0 = cj * kTile;
+    const int ntok = min(kTile, p.n_total - tok0);           // valid tokens (incl. the appended one)
+    const int ncopy = max(0, min(kTile, p.kv_len - tok0));   // of which bulk-copied from the cache
+    uint8_t* Ks = wsm + s * kStageBytes;
     uint8_t* Vs = Ks + kTileBytes;
-    __half* lg = ly->logits ? static_cast<__half*>(ly->logits) + static_cast<int64_t>(row) * p.logits_stride : nullptr;
 
-    const bool generic_writes = ntok < kStepTile || ncopy < ntok;
+    const bool generic_writes = ntok < kTile;                // only the last tile of a row
     if (generic_writes) {
       // zero the rows the copy does not write, so masked lanes multiply finite numbers
 #pragma unroll 1
@@ -387,18 +424,14 @@ __global__ void __launch_bounds__(kStepThreads, 1) decode_step_kernel(const Step
       constexpr int kChunks = kRowBytes / 16;
       const int r = p.kv_len - tok0;
       const int which = lane / kChunks, ch = lane % kChunks;
-      bool writer = (h % p.n_rep) == 0;
-      if (p.head_mask) {
-        const unsigned long long grp = (chm >> (kvh * p.n_rep)) & (p.n_rep >= 64 ? ~0ull : ((1ull << p.n_rep) - 1ull));
-        writer = h == kvh * p.n_rep + (__ffsll(static_cast<long long>(grp)) - 1);   // first live head of the kv group
-      }
+      const int bi = seg_row / p.H, kvh = (seg_row - bi * p.H) / p.n_rep;
 #pragma unroll 1
       for (int w = which; w < 2; w += 32 / kChunks) {
         const __half* src = static_cast<const __half*>(w ? ly->v_new : ly->k_new) +
                             (static_cast<int64_t>(bi) * p.H_kv + kvh) * D + ch * 8;
         const uint4 val = *reinterpret_cast<const uint4*>(src);
         *reinterpret_cast<uint4*>((w ? Vs : Ks) + r * kRowBytes + ch * 16) = val;
-        if (writer) {
+        if (seg_writer) {
           __half* dst = static_cast<__half*>(w ? ly->v_cache : ly->k_cache) + bi * p.stride_b + kvh * p.stride_h +
                         static_cast<int64_t>(p.kv_len) * D + ch * 8;
           *reinterpret_cast<uint4*>(dst) = val;
@@ -408,9 +441,9 @@ __global__ void __launch_bounds__(kStepThreads, 1) decode_step_kernel(const Step
     }
 
     // scores of the tile: rotated key rounded to fp16 after every elementwise op (:27), products summed in fp32
-    float d[kStepPasses];
+    float d[PASSES];
 #pragma unroll
-    for (int ps = 0; ps < kStepPasses; ++ps) {
+    for (int ps = 0; ps < PASSES; ++ps) {
       const int tl = ps * 4 + g;
       HV kl, kh;
       *reinterpret_cast<Vec*>(&kl) = *reinterpret_cast<const Vec*>(Ks + tl * kRowBytes + c * VB);
@@ -428,16 +461,24 @@ __global__ void __launch_bounds__(kStepThreads, 1) decode_step_kernel(const Step
       }
       d[ps] = d0 + d1;
     }
+
+    // ---- the RoPE registers are free: move the cursor on and fetch the NEXT tile's rows under the rest of this tile --
+    const bool was_last_of_range = cc.t == cc.t_end - 1;
+    cc.first = 0;
+    ++cc.t; ++cc.j;
+    if (cc.j == p.tpr || was_last_of_range) advance_slow(cc);
+    if (cc.l < p.L) load_table(cc.j * kTile, cs, sn);
+
 #pragma unroll
     for (int o = 1; o <= 4; o <<= 1) {
 #pragma unroll
-      for (int ps = 0; ps < kStepPasses; ++ps) d[ps] += __shfl_xor_sync(0xffffffffu, d[ps], o);
+      for (int ps = 0; ps < PASSES; ++ps) d[ps] += __shfl_xor_sync(0xffffffffu, d[ps], o);
     }
     // fp16 logit exactly as the reference forms it: fp16(matmul) / sqrt(D) -> fp16 (:111-113)
-    float sc[kStepPasses], pr[kStepPasses];
+    float sc[PASSES], pr[PASSES];
     float mx = -CUDART_INF_F;
 #pragma unroll
-    for (int ps = 0; ps < kStepPasses; ++ps) {
+    for (int ps = 0; ps < PASSES; ++ps) {
       const int tl = ps * 4 + g;
       const bool valid = tl < ntok;
       const __half s16 = __float2half_rn(div_by_const(__half2float(__float2half_rn(d[ps])), p.sqrt_d, p.rsqrt_d));
@@ -458,13 +499,13 @@ __global__ void __launch_bounds__(kStepThreads, 1) decode_step_kernel(const Step
         m = m_new;
       }
 #pragma unroll
-      for (int ps = 0; ps < kStepPasses; ++ps) {
+      for (int ps = 0; ps < PASSES; ++ps) {
         pr[ps] = fast_exp2((sc[ps] - m) * kLog2e);
         l += pr[ps];
       }
       // P.V (:138)
 #pragma unroll
-      for (int ps = 0; ps < kStepPasses; ++ps) {
+      for (int ps = 0; ps < PASSES; ++ps) {
         const int tl = ps * 4 + g;
         HV vl, vh;
         *reinterpret_cast<Vec*>(&vl) = *reinterpret_cast<const Vec*>(Vs + tl * kRowBytes + c * VB);
@@ -480,13 +521,11 @@ __global__ void __launch_bounds__(kStepThreads, 1) decode_step_kernel(const Step
       }
     }
 
-    // ---- stage s is free: refill it with the tile three ahead (possibly the next layer's) ------------------------
+    // ---- stage s is free: refill it with the tile STAGES ahead (possibly the next layer's) ---------------------------
     if (generic_writes) fence_proxy_async();         // generic-proxy writes above vs the async-proxy copy below
     __syncwarp();
-    if (ci.l < p.L) { issue(ci, s); advance(ci); }
-    s = (s + 1 == kStepStages) ? 0 : s + 1;
-#pragma unroll
-    for (int ps = 0; ps < kStepPasses; ++ps) { cs[ps] = csn[ps]; sn[ps] = snn[ps]; }
+    issue_next(s);
+    s = (s + 1 == STAGES) ? 0 : s + 1;
 
     if (!seg_end) continue;
 
@@ -512,27 +551,27 @@ __global__ void __launch_bounds__(kStepThreads, 1) decode_step_kernel(const Step
     }
     const int d0 = (g & 1) * (D / 2) + c * E2 + (g >> 1) * PER;   // first of the PER dims this lane now owns
 
-    // splits of this row: the virtual warps whose ranges intersect the row's tiles
-    const long long T = static_cast<long long>(p.b) * cnlh * p.tpr;
-    const long long weff = T < p.W ? T : p.W;
-    const int v = (gw + cl * kStepRot) % p.W;
-    const long long tf = static_cast<long long>(ci_row) * p.tpr;
+    // splits of this row: the virtual warps whose ranges intersect the row's tiles (32-bit: host checked T * W < 2^32)
+    const unsigned T = static_cast<unsigned>(p.b * seg_nlh * p.tpr);
+    const unsigned weff = T < static_cast<unsigned>(p.W) ? T : static_cast<unsigned>(p.W);
+    const int v = (gw + seg_l * kStepRot) % p.W;
+    const unsigned tf = static_cast<unsigned>(seg_i) * p.tpr;
     const int o_first = static_cast<int>(((tf + 1) * weff - 1) / T);
     const int o_last = static_cast<int>(((tf + p.tpr) * weff - 1) / T);
     const int n_seg = o_last - o_first + 1;
 
     if (n_seg == 1) {
-      emit_row(cl, row, bi, h, d0, fin, l > 0.f ? 1.f / l : 0.f, m);
+      emit_row(seg_l, seg_row, d0, fin, l > 0.f ? 1.f / l : 0.f, m);
       continue;
     }
     {
-      const int64_t slot = static_cast<int64_t>(cl) * p.slots + v + ci_row;
+      const int64_t slot = static_cast<int64_t>(seg_l) * p.slots + v + seg_i;
       *reinterpret_cast<PV_t*>(p.part + slot * D + d0) = *reinterpret_cast<const PV_t*>(fin);
       if (lane == 0) p.part_ml[slot] = make_float2(m, l);
     }
     __syncwarp();
     unsigned prev = 0;
-    unsigned int* ticket = p.tickets + static_cast<int64_t>(cl) * p.rows + row;
+    unsigned int* ticket = p.tickets + static_cast<int64_t>(seg_l) * p.rows + seg_row;
     if (lane == 0) {
       __threadfence();                                   // release: the partial is visible device-wide
       prev = atomicAdd(ticket, 1u);
@@ -543,14 +582,14 @@ __global__ void __launch_bounds__(kStepThreads, 1) decode_step_kernel(const Step
 
     // ---- last warp of the row: merge its n_seg partials (online over chunks of 32 splits) -----------------------
     {
-      const int64_t base = static_cast<int64_t>(cl) * p.slots + o_first + ci_row;
+      const int64_t base = static_cast<int64_t>(seg_l) * p.slots + o_first + seg_i;
       const float* rec = p.part + base * D + lane * PER;
       const float2* ml = p.part_ml + base;
       float M = -CUDART_INF_F, Lp = 0.f;
       float o[PER];
 #pragma unroll
       for (int k = 0; k < PER; ++k) o[k] = 0.f;
-      constexpr int kU = 16;                             // partial loads in flight per lane
+      constexpr int kU = WARPS > 8 ? 8 : 16;             // partial loads in flight per lane (register budget)
 #pragma unroll 1
       for (int c0 = 0; c0 < n_seg; c0 += 32) {
         const int nc = min(32, n_seg - c0);
@@ -585,7 +624,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) decode_step_kernel(const Step
       }
       const float Lsum = warp_sum(Lp);
       if (lane == 0) *ticket = 0;                        // self-cleaning ticket for the next step
-      emit_row(cl, row, bi, h, lane * PER, o, Lsum > 0.f ? 1.f / Lsum : 0.f, M);
+      emit_row(seg_l, seg_row, lane * PER, o, Lsum > 0.f ? 1.f / Lsum : 0.f, M);
     }
   }
 
@@ -603,28 +642,52 @@ __global__ void __launch_bounds__(kStepThreads, 1) decode_step_kernel(const Step
   }
 }
 
-template <int D>
+template <int D, int WARPS, int STAGES, int PASSES>
 constexpr size_t step_smem_bytes() {
-  return static_cast<size_t>(kStepWarps) * kStepStages * 2 * kStepTile * D * 2 + kStepWarps * kStepStages * 8 +
+  return static_cast<size_t>(WARPS) * STAGES * 2 * (4 * PASSES) * D * 2 + WARPS * STAGES * 8 +
          kStepSmemLayers * sizeof(SpattenStepLayer);
 }
 
+// Kernel variants: (warps per CTA, ring stages per warp).  192 KiB of K/V ring per SM either way.
+//   0: 8 warps x 3 stages x 16-token tiles     1: 16 warps x 3 stages x 8-token tiles (4 warps per scheduler, <= 128 regs)
+constexpr int kStepVariants = 2;
+constexpr int kStepMaxWarps = 16;
+using StepKernel = void (*)(const StepParams);
+struct StepVariant {
+  StepKernel kernel;
+  int warps, tile;
+  size_t smem;
+};
 template <int D>
-static int step_grid(int& grid) {
-  static int cached[64] = {};
+static StepVariant step_variant(int v) {
+  if (v == 1) return {decode_step_kernel<D, 16, 3, 2>, 16, 8, step_smem_bytes<D, 16, 3, 2>()};
+  return {decode_step_kernel<D, 8, 3, 4>, 8, 16, step_smem_bytes<D, 8, 3, 4>()};
+}
+static int step_variant_choice() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SPATTEN_STEP_VARIANT");      // tuning knob for tools/microbench.py; default 0
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v;
+}
+
+template <int D>
+static int step_grid(int variant, int& grid) {
+  static int cached[64][kStepVariants] = {};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 64 && cached[dev] > 0) { grid = cached[dev]; return SPATTEN_OK; }
-  cudaError_t e = cudaFuncSetAttribute(decode_step_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(step_smem_bytes<D>()));
+  if (dev < 64 && cached[dev][variant] > 0) { grid = cached[dev][variant]; return SPATTEN_OK; }
+  const StepVariant sv = step_variant<D>(variant);
+  cudaError_t e = cudaFuncSetAttribute(sv.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sv.smem));
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(decode_step_kernel)");
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_step_kernel<D>, kStepThreads, step_smem_bytes<D>());
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sv.kernel, sv.warps * 32, sv.smem);
   if (e != cudaSuccess || per_sm < 1) return cuda_fail(e, "decode_step_kernel does not fit on an SM");
   const int sms = sm_count();
   if (sms <= 0) return SPATTEN_ERR_CUDA;
   grid = sms;                                            // one persistent CTA per SM: all co-resident
-  if (dev < 64) cached[dev] = grid;
+  if (dev < 64) cached[dev][variant] = grid;
   return SPATTEN_OK;
 }
 
@@ -654,7 +717,7 @@ extern "C" size_t spatten_decode_step_workspace_bytes(int32_t num_layers, int32_
   if (num_layers <= 0 || batch <= 0 || num_heads <= 0 || (head_dim != 64 && head_dim != 128)) return 0;
   const int sms = sm_count();
   if (sms <= 0) return 0;
-  return step_workspace(num_layers, batch * num_heads, head_dim, sms * kStepWarps).total;
+  return step_workspace(num_layers, batch * num_heads, head_dim, sms * kStepMaxWarps).total;
 }
 
 extern "C" int spatten_decode_step(const SpattenStepArgs* a, void* stream) {
@@ -690,7 +753,9 @@ extern "C" int spatten_decode_step(const SpattenStepArgs* a, void* stream) {
   SPATTEN_CHECK_ARG(a->n_peers >= 0 && a->n_peers <= kStepMaxPeers, "spatten_decode_step: bad n_peers");
 
   int grid = 0;
-  if (int rc = (a->head_dim == 128 ? step_grid<128>(grid) : step_grid<64>(grid))) return rc;
+  const int variant = step_variant_choice();
+  if (int rc = (a->head_dim == 128 ? step_grid<128>(variant, grid) : step_grid<64>(variant, grid))) return rc;
+  const StepVariant sv = a->head_dim == 128 ? step_variant<128>(variant) : step_variant<64>(variant);
 
   StepParams p{};
   p.layers = a->layers;
@@ -711,13 +776,16 @@ extern "C" int spatten_decode_step(const SpattenStepArgs* a, void* stream) {
   p.q_pos = a->q_pos;
   p.head_mask = a->head_mask;
   p.head_importance = a->head_importance;
-  p.tpr = (n_total + kStepTile - 1) / kStepTile;
-  p.W = grid * kStepWarps;
+  p.W = grid * sv.warps;
+  p.tpr = (n_total + sv.tile - 1) / sv.tile;
   p.rows = static_cast<unsigned>(a->batch) * a->num_heads;
   p.sqrt_d = static_cast<float>(sqrt(static_cast<double>(a->head_dim)));
   p.rsqrt_d = 1.0f / p.sqrt_d;
 
-  const StepWorkspace w = step_workspace(p.L, static_cast<int>(p.rows), a->head_dim, p.W);
+  SPATTEN_CHECK_ARG(static_cast<double>(p.rows) * p.tpr * p.W < 4.0e9,
+                    "spatten_decode_step: batch * heads * tiles too large for the 32-bit work-list arithmetic");
+  // the layout is sized for the widest variant so that one workspace serves both
+  const StepWorkspace w = step_workspace(p.L, static_cast<int>(p.rows), a->head_dim, grid * kStepMaxWarps);
   if (a->workspace == nullptr || a->workspace_bytes < w.total) {
     set_error("spatten_decode_step: workspace %zu bytes < required %zu", a->workspace_bytes, w.total);
     return SPATTEN_ERR_WORKSPACE;
@@ -756,11 +824,10 @@ extern "C" int spatten_decode_step(const SpattenStepArgs* a, void* stream) {
 
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kStepThreads);
-  cfg.dynamicSmemBytes = a->head_dim == 128 ? step_smem_bytes<128>() : step_smem_bytes<64>();
+  cfg.blockDim = dim3(sv.warps * 32);
+  cfg.dynamicSmemBytes = sv.smem;
   cfg.stream = static_cast<cudaStream_t>(stream);
-  cudaError_t e = a->head_dim == 128 ? cudaLaunchKernelEx(&cfg, decode_step_kernel<128>, p)
-                                     : cudaLaunchKernelEx(&cfg, decode_step_kernel<64>, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, sv.kernel, p);
   if (e != cudaSuccess) return cuda_fail(e, "decode_step_kernel launch");
   return SPATTEN_OK;
 }

@@ -129,3 +129,39 @@ def build_prune_inputs(c: PruneCase) -> dict:
         scores.append(s.to(dt))
         past.append((k, v))
     return {"past": past, "scores": scores}
+
+
+@dataclass(frozen=True)
+class ChainCase:
+    """Decode step -> prune on the step's OWN attn_scores (run_spatten_llama.py:74-79): the keep set is derived from
+    the logits the forward itself produced, so logit parity and selection parity are tested as one chain."""
+    name: str
+    H: int
+    D: int
+    past: int          # cached tokens before the decode step (the step appends one)
+    start: int
+    important: int
+    recent: int
+    num_coming: int
+    seed: int
+
+
+CHAIN_CASES = [
+    ChainCase("g2s_129_to_64", 12, 64, 128, 4, 30, 30, 0, 301),              # configs[0] dims
+    ChainCase("d128_516_to_204", 8, 128, 515, 4, 100, 100, 0, 302),
+    ChainCase("demo_defaults_700", 8, 128, 699, 0, 150, 150, 90, 303),       # run_spatten_llama.py:134-136 defaults
+    ChainCase("c2_4096_to_2048", 32, 128, 4095, 4, 1022, 1022, 0, 304),      # BASELINE config 2, full size
+]
+
+
+def build_chain_inputs(c: ChainCase) -> dict:
+    dt = torch.float16
+    return {
+        "q": det_normal((1, c.H, 1, c.D), c.seed, 1.0, dt),
+        "k_new": det_normal((1, c.H, 1, c.D), c.seed + 1000, 1.0, dt),
+        "v_new": det_normal((1, c.H, 1, c.D), c.seed + 2000, 1.0, dt),
+        "past_k": det_normal((1, c.H, c.past, c.D), c.seed + 5000, 1.0, dt),
+        "past_v": det_normal((1, c.H, c.past, c.D), c.seed + 6000, 1.0, dt),
+        "position_ids": torch.full((1, 1), c.past, dtype=torch.int64),
+        "mask": torch.zeros((1, 1, 1, c.past + 1), dtype=dt),
+    }

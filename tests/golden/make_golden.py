@@ -25,7 +25,8 @@ sys.path.insert(0, "/root/reference")
 from spatten_llm.pos_shift.modify_llama import llama_pos_shift_attention_forward  # noqa: E402
 from spatten_llm.kv_cache_token_pruning import SpAttenKVCache                      # noqa: E402
 
-from cases import FWD_CASES, PRUNE_CASES, build_fwd_inputs, build_prune_inputs     # noqa: E402
+from cases import (CHAIN_CASES, FWD_CASES, PRUNE_CASES, build_chain_inputs, build_fwd_inputs,  # noqa: E402
+                   build_prune_inputs)
 
 
 class Rotary433(torch.nn.Module):
@@ -135,12 +136,46 @@ def run_prune(c):
     return res
 
 
+def run_chain(c):
+    """Reference decode step, then the reference prune on the attn_scores that step stashed (the demo's call pattern,
+    run_spatten_llama.py:74-79).  Stores the scores, the kept index set, and per head the gap between the k-th and
+    (k+1)-th candidate score (0 = a tie at the boundary, where torch.topk's choice is implementation-defined)."""
+    d = build_chain_inputs(c)
+    m = ShimAttention(c.H, c.H, c.D)
+    flat = lambda x: x.transpose(1, 2).reshape(1, 1, -1)
+    m.q_proj, m.k_proj, m.v_proj = Const(flat(d["q"])), Const(flat(d["k_new"])), Const(flat(d["v_new"]))
+    m.o_proj = torch.nn.Identity()
+    with torch.no_grad():
+        out, _, new_past = m(torch.zeros(1, 1, c.H * c.D, dtype=torch.float16), attention_mask=d["mask"],
+                             position_ids=d["position_ids"], past_key_value=(d["past_k"], d["past_v"]), use_cache=True)
+    scores = m.attn_scores                                        # [1, H, 1, S]
+    S = c.past + 1
+    cache = SpAttenKVCache(start_size=c.start, recent_size=c.recent, important_size=c.important, k_seq_dim=2, v_seq_dim=2)
+    kk = new_past[0].float().clone()
+    kk[..., 0] = torch.arange(S, dtype=torch.float32)[None, None, :]
+    coded = cache.apply_token_pruning([(kk, new_past[1].float())], c.num_coming, [scores.clone()])
+    kept = coded[0][0][0, :, :, 0].to(torch.int32)                # [H, keep_total]
+    cand = scores[0, :, 0, c.start: S - c.recent + c.num_coming].float()
+    srt = torch.sort(cand, dim=-1, descending=True).values
+    return {"out": out.numpy(), "attn_scores": scores.numpy(), "kept_idx": kept.numpy(),
+            "kth": srt[:, c.important - 1].numpy(), "next": srt[:, c.important].numpy()}
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(1)       # one thread => one summation order for the stored logits
+    only = sys.argv[1] if len(sys.argv) > 1 else None            # e.g. `make_golden.py chain`: (re)generate one family
+    if only == "chain":
+        for c in CHAIN_CASES:
+            np.savez_compressed(os.path.join(HERE, f"chain_{c.name}.npz"), **run_chain(c))
+            print("chain", c.name)
+        return
     for c in FWD_CASES:
         np.savez_compressed(os.path.join(HERE, f"fwd_{c.name}.npz"), **run_fwd(c))
         print("fwd", c.name)
+    for c in CHAIN_CASES:
+        np.savez_compressed(os.path.join(HERE, f"chain_{c.name}.npz"), **run_chain(c))
+        print("chain", c.name)
     for c in PRUNE_CASES:
         np.savez_compressed(os.path.join(HERE, f"prune_{c.name}.npz"), **run_prune(c))
         print("prune", c.name)

@@ -52,3 +52,45 @@ def assert_index_sets_match(mine: torch.Tensor, ref: torch.Tensor, score: torch.
         vals_r = sorted(score[h, only_r].tolist())
         assert vals_m == vals_r and len(set(vals_m)) == 1, (
             f"{what}: head {h} index sets differ outside a boundary tie: mine-only {only_m[:8]} ref-only {only_r[:8]}")
+
+
+def fp16_ulp(x: float) -> float:
+    """Spacing of fp16 numbers at magnitude |x| (normal range)."""
+    import math
+    ax = max(abs(float(x)), 2.0 ** -14)
+    return 2.0 ** (math.floor(math.log2(ax)) - 10)
+
+
+def assert_chain_sets_match(mine: torch.Tensor, ref_kept: torch.Tensor, ref_scores: torch.Tensor, kth: torch.Tensor,
+                            nxt: torch.Tensor, what="", slack_ulps: int = 2):
+    """Index-set parity for a keep set derived from the path's OWN logits (decode -> prune chain).
+
+    mine/ref_kept: [H, keep_total] ascending; ref_scores: [H, S] the REFERENCE's logits; kth/nxt: the reference's
+    k-th and (k+1)-th candidate scores per head.  The CUDA logits differ from the CPU reference's by one fp16 ulp on
+    ~0.1-1 % of entries (fp32 summation order), so: wherever the reference's boundary gap exceeds `slack_ulps` ulps
+    the sets must be IDENTICAL; elsewhere they may differ only by indices whose reference score lies within
+    `slack_ulps` ulps of the boundary (a tie or a one-ulp flip).  Returns a report dict.
+    """
+    mine, ref_kept, ref_scores = mine.cpu().long(), ref_kept.cpu().long(), ref_scores.cpu().float()
+    assert mine.shape == ref_kept.shape, f"{what}: shape {tuple(mine.shape)} vs {tuple(ref_kept.shape)}"
+    H = ref_kept.shape[0]
+    identical = flipped_heads = flipped_idx = wide_margin_heads = 0
+    for h in range(H):
+        ulp = fp16_ulp(float(kth[h]))
+        margin = float(kth[h]) - float(nxt[h])
+        wide = margin > slack_ulps * ulp
+        wide_margin_heads += int(wide)
+        if torch.equal(mine[h], ref_kept[h]):
+            identical += 1
+            continue
+        assert not wide, (f"{what}: head {h} differs although the reference's boundary gap {margin:.3e} is "
+                          f"{margin / ulp:.1f} ulp wide")
+        sm, sr = set(mine[h].tolist()), set(ref_kept[h].tolist())
+        diff = sorted(sm ^ sr)
+        off = (ref_scores[h, diff] - float(kth[h])).abs().max().item()
+        assert off <= slack_ulps * ulp + 1e-12, (
+            f"{what}: head {h}: index {diff[:6]} flipped but its reference score is {off / ulp:.1f} ulp from the boundary")
+        flipped_heads += 1
+        flipped_idx += len(diff) // 2
+    return {"heads": H, "identical": identical, "boundary_flips_heads": flipped_heads, "boundary_flips_idx": flipped_idx,
+            "heads_with_wide_margin": wide_margin_heads}

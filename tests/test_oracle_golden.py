@@ -90,3 +90,22 @@ def test_quant_planes_roundtrip():
     assert (full - x.float()).abs().max() <= 0.51 * sc.float().max()
     assert (coarse - x.float()).abs().max() <= 8.51 * sc.float().max()
     assert msb.shape == (2, 3, 17, 32) and msb.dtype == torch.uint8
+
+
+from cases import CHAIN_CASES, build_chain_inputs          # noqa: E402
+from helpers import assert_chain_sets_match                # noqa: E402
+
+
+@pytest.mark.parametrize("c", [c for c in CHAIN_CASES if c.past < 1000], ids=lambda c: c.name)
+def test_oracle_decode_then_prune_chain_matches_reference(c):
+    """The oracle's forward feeding the oracle's selection reproduces the reference's chained keep set."""
+    d, g = build_chain_inputs(c), load_golden("chain", c.name)
+    out, scores, (k, v) = O.attn_forward_core(d["q"], d["k_new"], d["v_new"], d["past_k"], d["past_v"],
+                                              d["position_ids"], d["mask"])
+    assert torch.equal(scores, g["attn_scores"])           # same library, same thread count: bit-identical logits
+    keep = O.select_keep_indices(O.importance_from_scores(scores), c.past + 1, c.start, c.important, c.recent, c.num_coming)
+    tail0 = c.past + 1 - c.recent + c.num_coming
+    full = torch.cat([torch.arange(c.start).expand(c.H, -1), keep,
+                      torch.arange(tail0, c.past + 1).expand(c.H, -1)], dim=1)
+    rep = assert_chain_sets_match(full, g["kept_idx"], g["attn_scores"][0, :, 0], g["kth"], g["next"], c.name, slack_ulps=0)
+    assert rep["identical"] + rep["boundary_flips_heads"] == c.H
