@@ -93,6 +93,18 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// Mixed-precision FMA of sm_100 (SASS FHFMA): c + a * b with fp16 a, b (selected halves of half2 registers, no
+// conversion instructions) and an fp32 accumulator.  The fp16 x fp16 product is exact in fp32, so the result is
+// bit-identical to fmaf(__half2float(a), __half2float(b), c).
+__device__ __forceinline__ float fhfma_lo(__half2 a, __half2 b, float c) {
+  asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(c) : "h"(__half_as_ushort(__low2half(a))), "h"(__half_as_ushort(__low2half(b))));
+  return c;
+}
+__device__ __forceinline__ float fhfma_hi(__half2 a, __half2 b, float c) {
+  asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(c) : "h"(__half_as_ushort(__high2half(a))), "h"(__half_as_ushort(__high2half(b))));
+  return c;
+}
+
 template <int BYTES>
 struct VecT;
 template <>

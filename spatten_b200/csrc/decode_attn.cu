@@ -292,15 +292,13 @@ __global__ void __launch_bounds__(kThreads, kPasses == 2 ? 2 : 1) decode_attn_ke
     load_query();
   }
 
-  // ---- rotate the query at its position id (modify_llama.py:92), fp16 op-for-op, keep as fp32 ---------
-  float ql[E2], qh[E2];
+  // ---- rotate the query at its position id (modify_llama.py:92), fp16 op-for-op; kept as fp16 (exactly the values
+  //      the reference forms) and fed to the mixed-precision FMA below -----------------------------------------------
+  HV qlr, qhr;
 #pragma unroll
   for (int i = 0; i < NH2; ++i) {
-    const __half2 rl = __hsub2_rn(__hmul2_rn(qa.h[i], qcs.h[i]), __hmul2_rn(qb.h[i], qsn.h[i]));
-    const __half2 rh = __hadd2_rn(__hmul2_rn(qb.h[i], qcs.h[i]), __hmul2_rn(qa.h[i], qsn.h[i]));
-    const float2 fl = __half22float2(rl), fh = __half22float2(rh);
-    ql[2 * i] = fl.x; ql[2 * i + 1] = fl.y;
-    qh[2 * i] = fh.x; qh[2 * i + 1] = fh.y;
+    qlr.h[i] = __hsub2_rn(__hmul2_rn(qa.h[i], qcs.h[i]), __hmul2_rn(qb.h[i], qsn.h[i]));
+    qhr.h[i] = __hadd2_rn(__hmul2_rn(qb.h[i], qcs.h[i]), __hmul2_rn(qa.h[i], qsn.h[i]));
   }
   STAMP(1);   // query rotated
 
@@ -370,11 +368,10 @@ __global__ void __launch_bounds__(kThreads, kPasses == 2 ? 2 : 1) decode_attn_ke
       for (int e = 0; e < NH2; ++e) {
         const __half2 rl = __hsub2_rn(__hmul2_rn(kl.h[e], cs[ps].h[e]), __hmul2_rn(kh.h[e], sn[ps].h[e]));
         const __half2 rh = __hadd2_rn(__hmul2_rn(kh.h[e], cs[ps].h[e]), __hmul2_rn(kl.h[e], sn[ps].h[e]));
-        const float2 fl = __half22float2(rl), fh = __half22float2(rh);
-        d0 = fmaf(ql[2 * e], fl.x, d0);
-        d0 = fmaf(ql[2 * e + 1], fl.y, d0);
-        d1 = fmaf(qh[2 * e], fh.x, d1);
-        d1 = fmaf(qh[2 * e + 1], fh.y, d1);
+        d0 = fhfma_lo(rl, qlr.h[e], d0);   // FHFMA: fp16 x fp16 product is exact in fp32, so these sums are bit-identical
+        d0 = fhfma_hi(rl, qlr.h[e], d0);   // to fmaf(float(q), float(k), d) -- without the 2 x 64 conversions per tile
+        d1 = fhfma_lo(rh, qhr.h[e], d1);
+        d1 = fhfma_hi(rh, qhr.h[e], d1);
       }
       d[ps] = d0 + d1;
     }
@@ -384,7 +381,7 @@ __global__ void __launch_bounds__(kThreads, kPasses == 2 ? 2 : 1) decode_attn_ke
       for (int ps = 0; ps < kPasses; ++ps) d[ps] += __shfl_xor_sync(0xffffffffu, d[ps], o);
     }
     // fp16 logit exactly as the reference forms it: fp16(matmul) / sqrt(D) -> fp16 (:111-113); mask (:132)
-    float sc[kPasses], pr[kPasses];
+    float sc[kPasses];
     float mx = -CUDART_INF_F;
 #pragma unroll
     for (int ps = 0; ps < kPasses; ++ps) {
@@ -409,10 +406,13 @@ __global__ void __launch_bounds__(kThreads, kPasses == 2 ? 2 : 1) decode_attn_ke
         for (int e = 0; e < E2; ++e) { accl[e] *= corr; acch[e] *= corr; }
         m = m_new;
       }
+      // probabilities enter P.V as fp16, as in the reference (softmax(...).to(fp16) @ V, :135-138); the running sum
+      // uses the same rounded values, so the final normalisation is exact for what was accumulated
+      __half2 ph[kPasses];
 #pragma unroll
       for (int ps = 0; ps < kPasses; ++ps) {
-        pr[ps] = fast_exp2((sc[ps] - m) * kLog2e);
-        l += pr[ps];
+        ph[ps] = __float2half2_rn(fast_exp2((sc[ps] - m) * kLog2e));
+        l += __low2float(ph[ps]);
       }
       // P.V (:138)
 #pragma unroll
@@ -423,11 +423,10 @@ __global__ void __launch_bounds__(kThreads, kPasses == 2 ? 2 : 1) decode_attn_ke
         *reinterpret_cast<Vec*>(&vh) = *reinterpret_cast<const Vec*>(Vs + tl * kRowBytes + D + c * VB);
 #pragma unroll
         for (int e = 0; e < NH2; ++e) {
-          const float2 fl = __half22float2(vl.h[e]), fh = __half22float2(vh.h[e]);
-          accl[2 * e] = fmaf(pr[ps], fl.x, accl[2 * e]);
-          accl[2 * e + 1] = fmaf(pr[ps], fl.y, accl[2 * e + 1]);
-          acch[2 * e] = fmaf(pr[ps], fh.x, acch[2 * e]);
-          acch[2 * e + 1] = fmaf(pr[ps], fh.y, acch[2 * e + 1]);
+          accl[2 * e] = fhfma_lo(vl.h[e], ph[ps], accl[2 * e]);
+          accl[2 * e + 1] = fhfma_hi(vl.h[e], ph[ps], accl[2 * e + 1]);
+          acch[2 * e] = fhfma_lo(vh.h[e], ph[ps], acch[2 * e]);
+          acch[2 * e + 1] = fhfma_hi(vh.h[e], ph[ps], acch[2 * e + 1]);
         }
       }
     }

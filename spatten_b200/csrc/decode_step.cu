@@ -36,7 +36,7 @@ namespace spatten {
 constexpr int kStepMaxPeers = 8;
 constexpr int kStepRot = 1;          // work-range rotation per layer (warps)
 constexpr int kStepCtrlWords = 64;   // workspace header: [0] steps completed, [1] exit ticket, [2] wait timed out
-constexpr int kStepSmemLayers = 128; // layer descriptors staged in shared memory when the model has at most this many
+constexpr int kStepSmemLayers = 96;  // layer descriptors staged in shared memory when the model has at most this many
 
 struct StepParams {
   const SpattenStepLayer* layers;
@@ -66,18 +66,19 @@ struct StepParams {
   int final_wait;          // wait for the last layer's flags before the kernel exits
   int sys_scope;           // flags live in peer memory
   float sqrt_d, rsqrt_d;
+  unsigned long long* dbg; // optional [L][grid][warps][8] globaltimer stamps (tools/microbench.py --step-timeline)
 };
 
-// Work-list cursor.  Every lane keeps the same copy; set_layer() ballots, so it is called warp-uniformly.
-struct Cursor {
-  int l;                   // layer (>= L: exhausted)
-  int t, t_end;            // this warp's tile range in the layer's live tile list
-  int j;                   // tile inside the current row
-  int i;                   // live row index
-  int bi, h;               // sequence and head of the current row
-  int first;               // 1 until the first tile of the range has been passed
+// CTA-level partial buffers in shared memory = segments a fast warp may run ahead of the slowest warp of its CTA
+__host__ __device__ constexpr int step_seg_bufs(int warps) { return warps <= 8 ? 6 : (warps <= 12 ? 4 : 3); }
+
+// One layer's share of work for a CTA: a contiguous range of the layer's (live row, tile) list.
+struct LayerRange {
+  int cs, ce;              // tile range [cs, ce) of this CTA
   int nlh;                 // live heads of the layer
-  unsigned long long hm;   // live head bits of the layer (valid when head_mask != nullptr)
+  int vcta;                // virtual CTA id (rotates with the layer)
+  unsigned T, geff;        // tiles in the layer, CTAs that take part
+  unsigned long long hm;   // live head bits (valid when head_mask != nullptr)
 };
 
 __device__ __forceinline__ int nth_set_bit64(unsigned long long m, int n) {
@@ -87,10 +88,10 @@ __device__ __forceinline__ int nth_set_bit64(unsigned long long m, int n) {
   return 32 + __fns(static_cast<unsigned>(m >> 32), 0, n - cl + 1);
 }
 
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* ptr, int sys) {
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned* ptr, int sys) {
   unsigned v;
-  if (sys) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
-  else asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  if (sys) asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  else asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
   return v;
 }
 
@@ -108,13 +109,24 @@ __device__ __forceinline__ void issue_kv_copies(bool pred, uint32_t k_dst, uint3
       : "memory");
 }
 
-template <int D, int WARPS, int STAGES, int PASSES>
+__device__ __forceinline__ unsigned long long step_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <int D, int WARPS, int STAGES, int PASSES, bool DBG = false>
 __global__ void __launch_bounds__(WARPS * 32, 1) decode_step_kernel(const StepParams p) {
+#define STAMP(layer, k)                                                                                                   \
+  do {                                                                                                                   \
+    if (DBG && p.dbg && lane == 0)                                                                                       \
+      p.dbg[((static_cast<size_t>(layer) * gridDim.x + blockIdx.x) * WARPS + warp) * 8 + (k)] = step_gtime();            \
+  } while (0)
   constexpr int kTile = 4 * PASSES;   // tokens per stage: PASSES passes of 4 keys x 8 lanes
   constexpr int E2 = D / 16;   // halves per lane in each half of the row (8 lanes cover D/2)
   constexpr int NH2 = E2 / 2;  // half2 per lane per half-row
   constexpr int VB = E2 * 2;   // bytes per lane per half-row
-  constexpr int PER = D / 32;  // output dims a lane owns after the reduce-scatter / in the merge
+  constexpr int PER = D / 32;  // output dims a lane owns after the reduce-scatter / in the merges
   using Vec = typename VecT<VB>::type;
   using HV = HalfVec<NH2>;
   using PV_t = typename VecT<PER * 4>::type;
@@ -122,91 +134,116 @@ __global__ void __launch_bounds__(WARPS * 32, 1) decode_step_kernel(const StepPa
   constexpr int kTileBytes = kTile * kRowBytes;
   constexpr int kStageBytes = 2 * kTileBytes;
   constexpr int kWarpSmem = STAGES * kStageBytes;
+  constexpr int kSegBufFloats = WARPS * D + WARPS * 2 + 4;      // partials, (m, l) pairs, {count, uses done, pad, pad}
 
   extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ unsigned cta_ctl[2];                    // [0] layers known complete, [1] layers somebody is polling for
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 3, c = lane & 7;
   uint8_t* wsm = smem + warp * kWarpSmem;
   const uint32_t wsm_u32 = smem_u32(wsm);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WARPS * kWarpSmem) + warp * STAGES;
   const uint32_t bars_u32 = smem_u32(bars);
-  const int gw = blockIdx.x * WARPS + warp;
+  float* segbuf = reinterpret_cast<float*>(smem + WARPS * kWarpSmem + WARPS * STAGES * 8);
+  SpattenStepLayer* lys_s = reinterpret_cast<SpattenStepLayer*>(segbuf + step_seg_bufs(WARPS) * kSegBufFloats);
 
-  // layer descriptors: 64 bytes each, read at every segment start / row change -- keep them on chip
+  // layer descriptors (64 bytes each, read at every segment start) and the segment buffers' control words
   const SpattenStepLayer* lys = p.layers;
   if (p.L <= kStepSmemLayers) {
-    uint4* dst = reinterpret_cast<uint4*>(smem + WARPS * kWarpSmem + WARPS * STAGES * 8);
+    uint4* dst = reinterpret_cast<uint4*>(lys_s);
     const uint4* src = reinterpret_cast<const uint4*>(p.layers);
     for (int k = threadIdx.x; k < p.L * 4; k += WARPS * 32) dst[k] = src[k];
-    lys = reinterpret_cast<const SpattenStepLayer*>(dst);
-    __syncthreads();
+    lys = lys_s;
   }
+  if (threadIdx.x < step_seg_bufs(WARPS) * 4)
+    reinterpret_cast<unsigned*>(segbuf + (threadIdx.x >> 2) * kSegBufFloats + WARPS * D + WARPS * 2)[threadIdx.x & 3] = 0u;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  if (threadIdx.x < 2) cta_ctl[threadIdx.x] = 0u;
+  __syncthreads();
 
   const unsigned epoch = *reinterpret_cast<volatile const unsigned*>(p.ctrl);
   const unsigned flag_target = (epoch + 1u) * p.rows;
+  const int G = gridDim.x;
 
-  // ---- cursors ------------------------------------------------------------------------------------------------
-  auto set_row = [&](Cursor& cu) {                       // (bi, h) of live row cu.i
-    cu.bi = cu.i / cu.nlh;
-    const int hidx = cu.i - cu.bi * cu.nlh;
-    cu.h = p.head_mask ? nth_set_bit64(cu.hm, hidx) : hidx;
-  };
-  auto set_layer = [&](Cursor& cu, int l) {
-    cu.l = l; cu.t = 0; cu.t_end = 0; cu.i = 0; cu.j = 0; cu.first = 1; cu.nlh = p.H; cu.hm = ~0ull; cu.bi = 0; cu.h = 0;
-    if (l >= p.L) return;
+  // ---- work split: layer l's tile list is cut into G contiguous CTA ranges; inside a CTA, warp w takes the tiles at
+  //      range positions w, w + WARPS, ... -- so the 8/16 warps of an SM work on neighbouring tiles of (mostly) one row
+  //      at the same time and their partials are combined on chip before anything goes to global memory ------------
+  auto layer_range = [&](int l) {
+    LayerRange r;
+    r.cs = r.ce = 0; r.nlh = p.H; r.hm = ~0ull; r.vcta = 0; r.T = 0; r.geff = 1;
+    if (l >= p.L) return r;
     if (p.head_mask) {
       const uint8_t* hr = p.head_mask + static_cast<size_t>(l) * p.H;
       const unsigned lo = __ballot_sync(0xffffffffu, lane < p.H && hr[lane] != 0);
       const unsigned hi = __ballot_sync(0xffffffffu, lane + 32 < p.H && hr[lane + 32] != 0);
-      cu.hm = static_cast<unsigned long long>(lo) | (static_cast<unsigned long long>(hi) << 32);
-      cu.nlh = __popcll(cu.hm);
+      r.hm = static_cast<unsigned long long>(lo) | (static_cast<unsigned long long>(hi) << 32);
+      r.nlh = __popcll(r.hm);
     }
-    const unsigned T = static_cast<unsigned>(p.b * cu.nlh * p.tpr);   // host checked: T * W < 2^32
-    const unsigned weff = T < static_cast<unsigned>(p.W) ? T : static_cast<unsigned>(p.W);
-    const unsigned v = static_cast<unsigned>(gw + l * kStepRot) % static_cast<unsigned>(p.W);
-    if (v < weff) {
-      cu.t = static_cast<int>(v * T / weff);
-      cu.t_end = static_cast<int>((v + 1) * T / weff);
-      cu.i = cu.t / p.tpr;
-      cu.j = cu.t - cu.i * p.tpr;
-      set_row(cu);
+    r.T = static_cast<unsigned>(p.b * r.nlh * p.tpr);            // host checked: T * G < 2^32
+    r.geff = r.T < static_cast<unsigned>(G) ? (r.T ? r.T : 1u) : static_cast<unsigned>(G);
+    r.vcta = static_cast<int>((blockIdx.x + static_cast<unsigned>(l) * kStepRot) % static_cast<unsigned>(G));
+    if (static_cast<unsigned>(r.vcta) < r.geff && r.T > 0) {
+      r.cs = static_cast<int>(static_cast<unsigned>(r.vcta) * r.T / r.geff);
+      r.ce = static_cast<int>((static_cast<unsigned>(r.vcta) + 1u) * r.T / r.geff);
     }
+    return r;
   };
-  // slow path of advance(): the row or the range ended
-  auto advance_slow = [&](Cursor& cu) {
-    if (cu.t >= cu.t_end) {
-      do set_layer(cu, cu.l + 1); while (cu.l < p.L && cu.t >= cu.t_end);
-    } else {
-      cu.j = 0;
-      ++cu.i;
-      set_row(cu);
-    }
+  auto row_coords = [&](int i, int nlh, unsigned long long hm, int& bi, int& h) {
+    bi = i / nlh;
+    const int hidx = i - bi * nlh;
+    h = p.head_mask ? nth_set_bit64(hm, hidx) : hidx;
   };
 
+  // ---- issue side: this warp's tile sequence, STAGES tiles ahead of the consumer, walking on across layers ----------
   const uint64_t pol = policy_evict_first();
-  // issue cursor: addresses of the tile it names
-  Cursor ci;
-  const __half* ik = nullptr;
-  const __half* iv = nullptr;
-  auto issue_ptrs = [&]() {
-    if (ci.l >= p.L) return;
-    const SpattenStepLayer* ly = lys + ci.l;
-    const int64_t off = ci.bi * p.stride_b + (ci.h / p.n_rep) * p.stride_h + static_cast<int64_t>(ci.j) * (kTile * D);
-    ik = static_cast<const __half*>(ly->k_cache) + off;
-    iv = static_cast<const __half*>(ly->v_cache) + off;
+  int il = 0, ik = 0, ike = 0;                   // layer, tile in the layer's list, end of the CTA's range
+  int ii = 0, ij = 0;                            // row and tile-in-row of tile ik
+  bool irow_new = true;                          // the pointers below have to be recomputed
+  int inlh = p.H;
+  unsigned long long ihm = ~0ull;
+  const __half* ikp = nullptr;                   // K / V address of row ii, tile 0
+  const __half* ivp = nullptr;
+  // this warp's tiles of layer l: range positions (warp + l) % WARPS, + WARPS, ... (the offset rotates with the layer so
+  // that the warps taking one tile more than the others change from layer to layer)
+  auto issue_enter = [&](int l) {
+    const LayerRange r = layer_range(l);
+    ik = r.cs + (warp + l) % WARPS; ike = r.ce; inlh = r.nlh; ihm = r.hm;
+    if (ik < ike) { ii = ik / p.tpr; ij = ik - ii * p.tpr; irow_new = true; }
   };
-  auto issue_next = [&](int s) {                          // copy the issue cursor's tile into stage s, move it on
-    if (ci.l >= p.L) return;
-    const int ncopy = min(kTile, p.kv_len - ci.j * kTile);
+  auto issue_seek = [&]() {                      // make (il, ik) name this warp's next tile, or il = L
+    while (il < p.L && ik >= ike) {
+      ++il;
+      if (il < p.L) issue_enter(il);
+    }
+  };
+  issue_enter(0);
+  issue_seek();
+  auto issue_next = [&](int s) {                 // copy the issue cursor's tile into stage s, move the cursor on
+    if (il >= p.L) return;
+    if (irow_new) {
+      int bi, h;
+      row_coords(ii, inlh, ihm, bi, h);
+      const SpattenStepLayer* ly = lys + il;
+      const int64_t off = bi * p.stride_b + (h / p.n_rep) * p.stride_h;
+      ikp = static_cast<const __half*>(ly->k_cache) + off;
+      ivp = static_cast<const __half*>(ly->v_cache) + off;
+      irow_new = false;
+    }
+    const int ncopy = min(kTile, p.kv_len - ij * kTile);
     if (ncopy > 0)
-      issue_kv_copies(lane == 0, wsm_u32 + s * kStageBytes, wsm_u32 + s * kStageBytes + kTileBytes, ik, iv,
+      issue_kv_copies(lane == 0, wsm_u32 + s * kStageBytes, wsm_u32 + s * kStageBytes + kTileBytes,
+                      ikp + static_cast<int64_t>(ij) * (kTile * D), ivp + static_cast<int64_t>(ij) * (kTile * D),
                       static_cast<uint32_t>(ncopy) * kRowBytes, bars_u32 + s * 8, pol);
-    ++ci.t; ++ci.j;
-    ik += kTile * D; iv += kTile * D;
-    if (ci.j == p.tpr || ci.t >= ci.t_end) { advance_slow(ci); issue_ptrs(); }
+    ik += WARPS; ij += WARPS;
+    while (ij >= p.tpr) { ij -= p.tpr; ++ii; irow_new = true; }
+    if (ik >= ike) issue_seek();
   };
 
-  // RoPE rows of one tile: cos | sin for the 4 passes of this lane's key group (L2 resident table)
+  // RoPE rows of one tile: cos | sin for the passes of this lane's key group (L2 resident table)
   auto load_table = [&](int tok0, HV (&cs)[PASSES], HV (&sn)[PASSES]) {
     if (tok0 + kTile <= p.rope_len) {
       const __half* r = p.rope + static_cast<int64_t>(tok0 + g) * D + c * E2;
@@ -226,15 +263,32 @@ __global__ void __launch_bounds__(WARPS * 32, 1) decode_step_kernel(const StepPa
     }
   };
 
+  // wait until every producer's flag of `layer` has reached this step's target (relaxed polls, one acquire fence)
+  // One warp per CTA polls the global flags (relaxed loads, one acquire fence) and tells the others through shared
+  // memory: 148 pollers on the flag's L2 line instead of every warp of the grid.
   auto wait_layer = [&](int layer) {
-    if (lane < p.wait_n) {
-      const unsigned* f = p.wait_flags + static_cast<int64_t>(layer) * p.wait_n + lane;
-      const long long tw = clock64();
-      while (static_cast<int>(ld_acquire(f, p.sys_scope) - flag_target) < 0) {
-        if (clock64() - tw > 4000000000ll) { atomicExch(p.ctrl + 2, 1u); break; }   // ~2 s: never wedge the GPU
+    volatile unsigned* seen = cta_ctl;               // layers [0, *seen) are known complete
+    if (*seen <= static_cast<unsigned>(layer)) {
+      unsigned mine = 0;
+      if (lane == 0) mine = atomicMax(cta_ctl + 1, static_cast<unsigned>(layer) + 1u) <= static_cast<unsigned>(layer);
+      mine = __shfl_sync(0xffffffffu, mine, 0);
+      if (mine) {
+        if (lane < p.wait_n) {
+          const unsigned* f = p.wait_flags + static_cast<int64_t>(layer) * p.wait_n + lane;
+          const long long tw = clock64();
+          while (static_cast<int>(ld_relaxed(f, p.sys_scope) - flag_target) < 0) {
+            if (clock64() - tw > 4000000000ll) { atomicExch(p.ctrl + 2, 1u); break; }   // ~2 s: never wedge the GPU
+          }
+        }
+        __syncwarp();
+        if (p.sys_scope) asm volatile("fence.acq_rel.sys;" ::: "memory");
+        else asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        if (lane == 0) atomicMax(cta_ctl, static_cast<unsigned>(layer) + 1u);
+      } else {
+        while (*seen <= static_cast<unsigned>(layer)) __nanosleep(20);
       }
     }
-    __syncwarp();
+    __threadfence_block();
   };
 
   // every lane stored its piece of a row of layer `layer`: publish it
@@ -248,8 +302,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) decode_step_kernel(const StepPa
     }
   };
 
-  // lane owns dims [d0, d0 + PER) of the finished row: normalise, round, store (locally or to every peer), side outputs
-  auto emit_row = [&](int layer, int row, int d0, const float (&o)[PER], float inv, float M) {
+  // lane owns dims [lane*PER, lane*PER + PER) of the finished row: normalise, round, store (locally or to every peer)
+  auto emit_row = [&](int layer, int row, const float (&o)[PER], float inv, float M) {
     __half oh16[PER];
     float habs = 0.f;
 #pragma unroll
@@ -257,7 +311,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) decode_step_kernel(const StepPa
       oh16[k] = __float2half_rn(o[k] * inv);
       habs += fabsf(__half2float(oh16[k]));
     }
-    const int64_t off = static_cast<int64_t>(row) * D + d0;
+    const int64_t off = static_cast<int64_t>(row) * D + lane * PER;
     if (p.n_out == 0) {
       __half* dst = static_cast<__half*>(lys[layer].out) + off;
       if (PER == 4) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(oh16);
@@ -289,19 +343,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) decode_step_kernel(const StepPa
   };
 
   // pruned heads of a layer: zero their output rows, keep the KV cache complete, count them as done
-  auto dead_rows = [&](int layer, int nlh, unsigned long long hm) {
+  auto dead_rows = [&](int layer, const LayerRange& R) {
     const SpattenStepLayer* ly = lys + layer;
-    const int ndh = p.H - nlh, n_dead = p.b * ndh;
-    const unsigned T = static_cast<unsigned>(p.b * nlh * p.tpr);
-    const int weff = static_cast<int>(T < static_cast<unsigned>(p.W) ? T : static_cast<unsigned>(p.W));
-    const int v = (gw + layer * kStepRot) % p.W;
+    const int ndh = p.H - R.nlh, n_dead = p.b * ndh;
+    if (static_cast<unsigned>(R.vcta) >= R.geff) return;       // CTAs without a range in this layer take no rows either
+    const int vw = R.vcta * WARPS + warp, nvw = static_cast<int>(R.geff) * WARPS;
     const unsigned long long hall = p.H >= 64 ? ~0ull : ((1ull << p.H) - 1ull);
 #pragma unroll 1
-    for (int dr = v; dr < n_dead; dr += weff) {
+    for (int dr = vw; dr < n_dead; dr += nvw) {
       const int dbi = dr / ndh;
-      const int dh = nth_set_bit64(~hm & hall, dr - dbi * ndh);
+      const int dh = nth_set_bit64(~R.hm & hall, dr - dbi * ndh);
       const int dkvh = dh / p.n_rep;
-      const unsigned long long grp = (hm >> (dkvh * p.n_rep)) & (p.n_rep >= 64 ? ~0ull : ((1ull << p.n_rep) - 1ull));
+      const unsigned long long grp = (R.hm >> (dkvh * p.n_rep)) & (p.n_rep >= 64 ? ~0ull : ((1ull << p.n_rep) - 1ull));
       if (p.append && grp == 0 && dh == dkvh * p.n_rep) {
         constexpr int kChunks = kRowBytes / 16;
         const int which = lane / kChunks, ch = lane % kChunks;
@@ -317,314 +370,348 @@ __global__ void __launch_bounds__(WARPS * 32, 1) decode_step_kernel(const StepPa
       float z[PER];
 #pragma unroll
       for (int k = 0; k < PER; ++k) z[k] = 0.f;
-      emit_row(layer, dbi * p.H + dh, lane * PER, z, 0.f, -CUDART_INF_F);
+      emit_row(layer, dbi * p.H + dh, z, 0.f, -CUDART_INF_F);
     }
   };
 
   // ---- pipeline prologue ----------------------------------------------------------------------------------------
-  Cursor cc;
-  set_layer(cc, 0);
-  while (cc.l < p.L && cc.t >= cc.t_end) set_layer(cc, cc.l + 1);
-  ci = cc;
-  issue_ptrs();
-  if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
-    fence_mbar_init();
-  }
-  __syncwarp();
 #pragma unroll 1
   for (int s = 0; s < STAGES; ++s) issue_next(s);
 
   unsigned phase = 0;     // bit s = parity the next wait on stage s uses
   int s = 0;
-  float ql[E2], qh[E2], accl[E2], acch[E2];
-  float m = -CUDART_INF_F, l = 0.f;
-  HV cs[PASSES], sn[PASSES];
-  if (cc.l < p.L) load_table(cc.j * kTile, cs, sn);
-  // segment constants (a segment = this warp's tiles of one row)
-  int seg_l = 0, seg_row = 0, seg_i = 0, seg_nlh = p.H;
-  bool seg_writer = false;
-  const SpattenStepLayer* ly = lys;
-  __half* lg = nullptr;
+  unsigned seg_seq = 0;   // segments (CTA range x row) this CTA has walked past: selects the shared-memory buffer
 
 #pragma unroll 1
-  while (cc.l < p.L) {
-    const int cj = cc.j;
-    if (cc.first | (cj == 0)) {
-      // ---- segment start ------------------------------------------------------------------------------------------
-      seg_l = cc.l; seg_i = cc.i; seg_nlh = cc.nlh;
-      const int bi = cc.bi, h = cc.h;
-      seg_row = bi * p.H + h;
-      ly = lys + seg_l;
-      if (cc.first) {
+  for (int l = 0; l < p.L; ++l) {
+    const LayerRange R = layer_range(l);
+    const SpattenStepLayer* ly = lys + l;
+    bool waited = !(l > 0 && p.chain);
+    if (p.head_mask && R.nlh < p.H && R.T > 0) {
+      // the appended rows of fully pruned kv groups come from this layer's projections: same dependency as the query
+      if (!waited) { wait_layer(l - 1); waited = true; }
+      dead_rows(l, R);
+    }
+    if (R.cs >= R.ce) continue;
+    const int i0 = R.cs / p.tpr, i1 = (R.ce - 1) / p.tpr;
+    int k = R.cs + (warp + l) % WARPS;                     // this warp's next tile in the layer's list
+
+#pragma unroll 1
+    for (int i = i0; i <= i1; ++i, ++seg_seq) {
+      // ---- one segment: the part of row i inside this CTA's range; this warp's tiles of it --------------------------
+      const int row_end = min(R.ce, (i + 1) * p.tpr);
+      const bool have = k < row_end;
+      int bi, h;
+      row_coords(i, R.nlh, R.hm, bi, h);
+      const int row = bi * p.H + h;
+      float fin[PER];
+      float m = -CUDART_INF_F, lsum = 0.f;
+      if (have) {
         // the decoder's dependency: layer l's query exists only when every row of layer l-1 has been stored
-        if (seg_l > 0 && p.chain) wait_layer(seg_l - 1);
-        if (p.head_mask && seg_nlh < p.H) dead_rows(seg_l, seg_nlh, cc.hm);
-      }
-      seg_writer = (h % p.n_rep) == 0;
-      if (p.head_mask) {
-        const int kvh = h / p.n_rep;
-        const unsigned long long grp = (cc.hm >> (kvh * p.n_rep)) & (p.n_rep >= 64 ? ~0ull : ((1ull << p.n_rep) - 1ull));
-        seg_writer = h == kvh * p.n_rep + (__ffsll(static_cast<long long>(grp)) - 1);   // first live head of the kv group
-      }
-      lg = ly->logits ? static_cast<__half*>(ly->logits) + static_cast<int64_t>(seg_row) * p.logits_stride : nullptr;
-      // query of this row, rotated at its position id (modify_llama.py:92), fp16 op-for-op, kept as fp32
-      int64_t pos = p.q_pos ? p.q_pos[bi] : p.kv_len;
-      pos = max(static_cast<int64_t>(0), min(pos, static_cast<int64_t>(p.rope_len - 1)));
-      const __half* qr = static_cast<const __half*>(ly->q) + static_cast<int64_t>(seg_row) * D;
-      HV qa, qb, qcs, qsn;
-      *reinterpret_cast<Vec*>(&qa) = *reinterpret_cast<const Vec*>(qr + c * E2);
-      *reinterpret_cast<Vec*>(&qb) = *reinterpret_cast<const Vec*>(qr + D / 2 + c * E2);
-      *reinterpret_cast<Vec*>(&qcs) = __ldg(reinterpret_cast<const Vec*>(p.rope + pos * D + c * E2));
-      *reinterpret_cast<Vec*>(&qsn) = __ldg(reinterpret_cast<const Vec*>(p.rope + pos * D + D / 2 + c * E2));
+        STAMP(l, 0);                                       // segment reached
+        if (!waited) { wait_layer(l - 1); waited = true; }
+        STAMP(l, 1);                                       // previous layer complete (chain)
+        int j = k - i * p.tpr;
+        HV cs[PASSES], sn[PASSES];
+        load_table(j * kTile, cs, sn);
+        // query of this row, rotated at its position id (modify_llama.py:92), fp16 op-for-op, kept as fp32
+        HV qlr, qhr;                                      // rotated query, exactly the fp16 values the reference forms
+        float accl[E2], acch[E2];
+        {
+          int64_t pos = p.q_pos ? p.q_pos[bi] : p.kv_len;
+          pos = max(static_cast<int64_t>(0), min(pos, static_cast<int64_t>(p.rope_len - 1)));
+          const __half* qr = static_cast<const __half*>(ly->q) + static_cast<int64_t>(row) * D;
+          HV qa, qb, qcs, qsn;
+          *reinterpret_cast<Vec*>(&qa) = *reinterpret_cast<const Vec*>(qr + c * E2);
+          *reinterpret_cast<Vec*>(&qb) = *reinterpret_cast<const Vec*>(qr + D / 2 + c * E2);
+          *reinterpret_cast<Vec*>(&qcs) = __ldg(reinterpret_cast<const Vec*>(p.rope + pos * D + c * E2));
+          *reinterpret_cast<Vec*>(&qsn) = __ldg(reinterpret_cast<const Vec*>(p.rope + pos * D + D / 2 + c * E2));
 #pragma unroll
-      for (int k = 0; k < NH2; ++k) {
-        const __half2 rl = __hsub2_rn(__hmul2_rn(qa.h[k], qcs.h[k]), __hmul2_rn(qb.h[k], qsn.h[k]));
-        const __half2 rh = __hadd2_rn(__hmul2_rn(qb.h[k], qcs.h[k]), __hmul2_rn(qa.h[k], qsn.h[k]));
-        const float2 fl = __half22float2(rl), fh = __half22float2(rh);
-        ql[2 * k] = fl.x; ql[2 * k + 1] = fl.y;
-        qh[2 * k] = fh.x; qh[2 * k + 1] = fh.y;
-      }
-      m = -CUDART_INF_F;
-      l = 0.f;
-#pragma unroll
-      for (int k = 0; k < E2; ++k) accl[k] = acch[k] = 0.f;
-    }
-    const bool seg_end = (cj == p.tpr - 1) | (cc.t == cc.t_end - 1);
-
-    // ---- one tile -------------------------------------------------------------------------------------------------
-    const int tok0 = cj * kTile;
-    const int ntok = min(kTile, p.n_total - tok0);           // valid tokens (incl. the appended one)
-    const int ncopy = max(0, min(kTile, p.kv_len - tok0));   // of which bulk-copied from the cache
-    uint8_t* Ks = wsm + s * kStageBytes;
-    uint8_t* Vs = Ks + kTileBytes;
-
-    const bool generic_writes = ntok < kTile;                // only the last tile of a row
-    if (generic_writes) {
-      // zero the rows the copy does not write, so masked lanes multiply finite numbers
-#pragma unroll 1
-      for (int o = ncopy * kRowBytes + lane * 16; o < kTileBytes; o += 32 * 16) {
-        *reinterpret_cast<uint4*>(Ks + o) = make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(Vs + o) = make_uint4(0, 0, 0, 0);
-      }
-      __syncwarp();
-    }
-    if (ncopy > 0) {
-      if (!mbar_try_wait(&bars[s], (phase >> s) & 1u)) {
-        const long long tw = clock64();
-        while (!mbar_try_wait(&bars[s], (phase >> s) & 1u)) {
-          if (clock64() - tw > 4000000000ll) __trap();    // a lost copy must fail the launch, not wedge the GPU
-        }
-      }
-      phase ^= 1u << s;
-    }
-    if (ncopy < ntok) {
-      // the appended token (modify_llama.py:95-100): its un-rotated K/V row goes into the tile and into slot kv_len
-      constexpr int kChunks = kRowBytes / 16;
-      const int r = p.kv_len - tok0;
-      const int which = lane / kChunks, ch = lane % kChunks;
-      const int bi = seg_row / p.H, kvh = (seg_row - bi * p.H) / p.n_rep;
-#pragma unroll 1
-      for (int w = which; w < 2; w += 32 / kChunks) {
-        const __half* src = static_cast<const __half*>(w ? ly->v_new : ly->k_new) +
-                            (static_cast<int64_t>(bi) * p.H_kv + kvh) * D + ch * 8;
-        const uint4 val = *reinterpret_cast<const uint4*>(src);
-        *reinterpret_cast<uint4*>((w ? Vs : Ks) + r * kRowBytes + ch * 16) = val;
-        if (seg_writer) {
-          __half* dst = static_cast<__half*>(w ? ly->v_cache : ly->k_cache) + bi * p.stride_b + kvh * p.stride_h +
-                        static_cast<int64_t>(p.kv_len) * D + ch * 8;
-          *reinterpret_cast<uint4*>(dst) = val;
-        }
-      }
-      __syncwarp();
-    }
-
-    // scores of the tile: rotated key rounded to fp16 after every elementwise op (:27), products summed in fp32
-    float d[PASSES];
-#pragma unroll
-    for (int ps = 0; ps < PASSES; ++ps) {
-      const int tl = ps * 4 + g;
-      HV kl, kh;
-      *reinterpret_cast<Vec*>(&kl) = *reinterpret_cast<const Vec*>(Ks + tl * kRowBytes + c * VB);
-      *reinterpret_cast<Vec*>(&kh) = *reinterpret_cast<const Vec*>(Ks + tl * kRowBytes + D + c * VB);
-      float d0 = 0.f, d1 = 0.f;
-#pragma unroll
-      for (int e = 0; e < NH2; ++e) {
-        const __half2 rl = __hsub2_rn(__hmul2_rn(kl.h[e], cs[ps].h[e]), __hmul2_rn(kh.h[e], sn[ps].h[e]));
-        const __half2 rh = __hadd2_rn(__hmul2_rn(kh.h[e], cs[ps].h[e]), __hmul2_rn(kl.h[e], sn[ps].h[e]));
-        const float2 fl = __half22float2(rl), fh = __half22float2(rh);
-        d0 = fmaf(ql[2 * e], fl.x, d0);
-        d0 = fmaf(ql[2 * e + 1], fl.y, d0);
-        d1 = fmaf(qh[2 * e], fh.x, d1);
-        d1 = fmaf(qh[2 * e + 1], fh.y, d1);
-      }
-      d[ps] = d0 + d1;
-    }
-
-    // ---- the RoPE registers are free: move the cursor on and fetch the NEXT tile's rows under the rest of this tile --
-    const bool was_last_of_range = cc.t == cc.t_end - 1;
-    cc.first = 0;
-    ++cc.t; ++cc.j;
-    if (cc.j == p.tpr || was_last_of_range) advance_slow(cc);
-    if (cc.l < p.L) load_table(cc.j * kTile, cs, sn);
-
-#pragma unroll
-    for (int o = 1; o <= 4; o <<= 1) {
-#pragma unroll
-      for (int ps = 0; ps < PASSES; ++ps) d[ps] += __shfl_xor_sync(0xffffffffu, d[ps], o);
-    }
-    // fp16 logit exactly as the reference forms it: fp16(matmul) / sqrt(D) -> fp16 (:111-113)
-    float sc[PASSES], pr[PASSES];
-    float mx = -CUDART_INF_F;
-#pragma unroll
-    for (int ps = 0; ps < PASSES; ++ps) {
-      const int tl = ps * 4 + g;
-      const bool valid = tl < ntok;
-      const __half s16 = __float2half_rn(div_by_const(__half2float(__float2half_rn(d[ps])), p.sqrt_d, p.rsqrt_d));
-      if (valid && c == 0 && lg) lg[tok0 + tl] = s16;
-      sc[ps] = valid ? __half2float(s16) : -CUDART_INF_F;
-      mx = fmaxf(mx, sc[ps]);
-    }
-    // online softmax (:135): m is warp-uniform; l and acc are per key group until the segment ends
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
-    const float m_new = fmaxf(m, mx);
-    if (m_new > -CUDART_INF_F) {
-      if (m_new != m) {
-        const float corr = fast_exp2((m - m_new) * kLog2e);
-        l *= corr;
-#pragma unroll
-        for (int e = 0; e < E2; ++e) { accl[e] *= corr; acch[e] *= corr; }
-        m = m_new;
-      }
-#pragma unroll
-      for (int ps = 0; ps < PASSES; ++ps) {
-        pr[ps] = fast_exp2((sc[ps] - m) * kLog2e);
-        l += pr[ps];
-      }
-      // P.V (:138)
-#pragma unroll
-      for (int ps = 0; ps < PASSES; ++ps) {
-        const int tl = ps * 4 + g;
-        HV vl, vh;
-        *reinterpret_cast<Vec*>(&vl) = *reinterpret_cast<const Vec*>(Vs + tl * kRowBytes + c * VB);
-        *reinterpret_cast<Vec*>(&vh) = *reinterpret_cast<const Vec*>(Vs + tl * kRowBytes + D + c * VB);
-#pragma unroll
-        for (int e = 0; e < NH2; ++e) {
-          const float2 fl = __half22float2(vl.h[e]), fh = __half22float2(vh.h[e]);
-          accl[2 * e] = fmaf(pr[ps], fl.x, accl[2 * e]);
-          accl[2 * e + 1] = fmaf(pr[ps], fl.y, accl[2 * e + 1]);
-          acch[2 * e] = fmaf(pr[ps], fh.x, acch[2 * e]);
-          acch[2 * e + 1] = fmaf(pr[ps], fh.y, acch[2 * e + 1]);
-        }
-      }
-    }
-
-    // ---- stage s is free: refill it with the tile STAGES ahead (possibly the next layer's) ---------------------------
-    if (generic_writes) fence_proxy_async();         // generic-proxy writes above vs the async-proxy copy below
-    __syncwarp();
-    issue_next(s);
-    s = (s + 1 == STAGES) ? 0 : s + 1;
-
-    if (!seg_end) continue;
-
-    // ---- segment finished: reduce-scatter over the 4 key groups (lanes that differ in bits 3 and 4) -------------
-    l += __shfl_xor_sync(0xffffffffu, l, 8);
-    l += __shfl_xor_sync(0xffffffffu, l, 16);
-    float keep[E2], fin[PER];
-    {
-      const bool up = (g & 1) != 0;                 // bit 3: keep the upper half-row, send the lower
-#pragma unroll
-      for (int e = 0; e < E2; ++e) {
-        const float send = up ? accl[e] : acch[e];
-        const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
-        keep[e] = (up ? acch[e] : accl[e]) + recv;
-      }
-      const bool up2 = (g & 2) != 0;                // bit 4: keep the upper PER of the E2 values
-#pragma unroll
-      for (int e = 0; e < PER; ++e) {
-        const float send = up2 ? keep[e] : keep[e + PER];
-        const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
-        fin[e] = (up2 ? keep[e + PER] : keep[e]) + recv;
-      }
-    }
-    const int d0 = (g & 1) * (D / 2) + c * E2 + (g >> 1) * PER;   // first of the PER dims this lane now owns
-
-    // splits of this row: the virtual warps whose ranges intersect the row's tiles (32-bit: host checked T * W < 2^32)
-    const unsigned T = static_cast<unsigned>(p.b * seg_nlh * p.tpr);
-    const unsigned weff = T < static_cast<unsigned>(p.W) ? T : static_cast<unsigned>(p.W);
-    const int v = (gw + seg_l * kStepRot) % p.W;
-    const unsigned tf = static_cast<unsigned>(seg_i) * p.tpr;
-    const int o_first = static_cast<int>(((tf + 1) * weff - 1) / T);
-    const int o_last = static_cast<int>(((tf + p.tpr) * weff - 1) / T);
-    const int n_seg = o_last - o_first + 1;
-
-    if (n_seg == 1) {
-      emit_row(seg_l, seg_row, d0, fin, l > 0.f ? 1.f / l : 0.f, m);
-      continue;
-    }
-    {
-      const int64_t slot = static_cast<int64_t>(seg_l) * p.slots + v + seg_i;
-      *reinterpret_cast<PV_t*>(p.part + slot * D + d0) = *reinterpret_cast<const PV_t*>(fin);
-      if (lane == 0) p.part_ml[slot] = make_float2(m, l);
-    }
-    __syncwarp();
-    unsigned prev = 0;
-    unsigned int* ticket = p.tickets + static_cast<int64_t>(seg_l) * p.rows + seg_row;
-    if (lane == 0) {
-      __threadfence();                                   // release: the partial is visible device-wide
-      prev = atomicAdd(ticket, 1u);
-    }
-    prev = __shfl_sync(0xffffffffu, prev, 0);
-    if (prev != static_cast<unsigned>(n_seg - 1)) continue;
-    __threadfence();                                     // acquire side
-
-    // ---- last warp of the row: merge its n_seg partials (online over chunks of 32 splits) -----------------------
-    {
-      const int64_t base = static_cast<int64_t>(seg_l) * p.slots + o_first + seg_i;
-      const float* rec = p.part + base * D + lane * PER;
-      const float2* ml = p.part_ml + base;
-      float M = -CUDART_INF_F, Lp = 0.f;
-      float o[PER];
-#pragma unroll
-      for (int k = 0; k < PER; ++k) o[k] = 0.f;
-      constexpr int kU = WARPS > 8 ? 8 : 16;             // partial loads in flight per lane (register budget)
-#pragma unroll 1
-      for (int c0 = 0; c0 < n_seg; c0 += 32) {
-        const int nc = min(32, n_seg - c0);
-        const float2 mlj = lane < nc ? __ldcg(ml + c0 + lane) : make_float2(-CUDART_INF_F, 0.f);
-        PV_t vv[kU];
-#pragma unroll
-        for (int u = 0; u < kU; ++u)
-          vv[u] = __ldcg(reinterpret_cast<const PV_t*>(rec + static_cast<int64_t>(c0 + min(u, nc - 1)) * D));
-        const float Mn = fmaxf(M, warp_max(mlj.x));
-        const float corr = (Mn > -CUDART_INF_F) ? fast_exp2((M - Mn) * kLog2e) : 0.f;   // M = -inf -> 0
-        const float wj = (Mn > -CUDART_INF_F) ? fast_exp2((mlj.x - Mn) * kLog2e) : 0.f;
-        Lp = fmaf(mlj.y, wj, Lp * corr);
-#pragma unroll
-        for (int k = 0; k < PER; ++k) o[k] *= corr;
-        M = Mn;
-#pragma unroll 1
-        for (int u0 = 0; u0 < nc; u0 += kU) {
-          if (u0 > 0) {
-#pragma unroll
-            for (int u = 0; u < kU; ++u)
-              vv[u] = __ldcg(reinterpret_cast<const PV_t*>(rec + static_cast<int64_t>(c0 + min(u0 + u, nc - 1)) * D));
+          for (int e = 0; e < NH2; ++e) {
+            qlr.h[e] = __hsub2_rn(__hmul2_rn(qa.h[e], qcs.h[e]), __hmul2_rn(qb.h[e], qsn.h[e]));
+            qhr.h[e] = __hadd2_rn(__hmul2_rn(qb.h[e], qcs.h[e]), __hmul2_rn(qa.h[e], qsn.h[e]));
           }
+        }
+#pragma unroll
+        for (int e = 0; e < E2; ++e) accl[e] = acch[e] = 0.f;
+        const int kvh = h / p.n_rep;
+        bool writer = (h % p.n_rep) == 0;
+        if (p.head_mask) {
+          const unsigned long long grp = (R.hm >> (kvh * p.n_rep)) & (p.n_rep >= 64 ? ~0ull : ((1ull << p.n_rep) - 1ull));
+          writer = h == kvh * p.n_rep + (__ffsll(static_cast<long long>(grp)) - 1);   // first live head of the kv group
+        }
+        __half* lg = ly->logits ? static_cast<__half*>(ly->logits) + static_cast<int64_t>(row) * p.logits_stride : nullptr;
+
+#pragma unroll 1
+        for (; k < row_end; k += WARPS, j += WARPS) {
+          // ---- one tile ---------------------------------------------------------------------------------------------
+          const int tok0 = j * kTile;
+          const int ntok = min(kTile, p.n_total - tok0);           // valid tokens (incl. the appended one)
+          const int ncopy = max(0, min(kTile, p.kv_len - tok0));   // of which bulk-copied from the cache
+          uint8_t* Ks = wsm + s * kStageBytes;
+          uint8_t* Vs = Ks + kTileBytes;
+
+          const bool generic_writes = ntok < kTile;                // only the last tile of a row
+          if (generic_writes) {
+            // zero the rows the copy does not write, so masked lanes multiply finite numbers
+#pragma unroll 1
+            for (int o = ncopy * kRowBytes + lane * 16; o < kTileBytes; o += 32 * 16) {
+              *reinterpret_cast<uint4*>(Ks + o) = make_uint4(0, 0, 0, 0);
+              *reinterpret_cast<uint4*>(Vs + o) = make_uint4(0, 0, 0, 0);
+            }
+            __syncwarp();
+          }
+          if (ncopy > 0) {
+            if (!mbar_try_wait(&bars[s], (phase >> s) & 1u)) {
+              const long long tw = clock64();
+              while (!mbar_try_wait(&bars[s], (phase >> s) & 1u)) {
+                if (clock64() - tw > 4000000000ll) __trap();    // a lost copy must fail the launch, not wedge the GPU
+              }
+            }
+            phase ^= 1u << s;
+          }
+          if (DBG && k == R.cs + (warp + l) % WARPS) STAMP(l, 2);   // first tile of the layer landed, query rotated
+          if (ncopy < ntok) {
+            // the appended token (modify_llama.py:95-100): its un-rotated K/V row goes into the tile and into slot kv_len
+            constexpr int kChunks = kRowBytes / 16;
+            const int r = p.kv_len - tok0;
+            const int which = lane / kChunks, ch = lane % kChunks;
+#pragma unroll 1
+            for (int w = which; w < 2; w += 32 / kChunks) {
+              const __half* src = static_cast<const __half*>(w ? ly->v_new : ly->k_new) +
+                                  (static_cast<int64_t>(bi) * p.H_kv + kvh) * D + ch * 8;
+              const uint4 val = *reinterpret_cast<const uint4*>(src);
+              *reinterpret_cast<uint4*>((w ? Vs : Ks) + r * kRowBytes + ch * 16) = val;
+              if (writer) {
+                __half* dst = static_cast<__half*>(w ? ly->v_cache : ly->k_cache) + bi * p.stride_b + kvh * p.stride_h +
+                              static_cast<int64_t>(p.kv_len) * D + ch * 8;
+                *reinterpret_cast<uint4*>(dst) = val;
+              }
+            }
+            __syncwarp();
+          }
+
+          // scores of the tile: rotated key rounded to fp16 after every elementwise op (:27), products summed in fp32
+          float d[PASSES];
+#pragma unroll
+          for (int ps = 0; ps < PASSES; ++ps) {
+            const int tl = ps * 4 + g;
+            HV kl, kh;
+            *reinterpret_cast<Vec*>(&kl) = *reinterpret_cast<const Vec*>(Ks + tl * kRowBytes + c * VB);
+            *reinterpret_cast<Vec*>(&kh) = *reinterpret_cast<const Vec*>(Ks + tl * kRowBytes + D + c * VB);
+            float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+            for (int e = 0; e < NH2; ++e) {
+              const __half2 rl = __hsub2_rn(__hmul2_rn(kl.h[e], cs[ps].h[e]), __hmul2_rn(kh.h[e], sn[ps].h[e]));
+              const __half2 rh = __hadd2_rn(__hmul2_rn(kh.h[e], cs[ps].h[e]), __hmul2_rn(kl.h[e], sn[ps].h[e]));
+              d0 = fhfma_lo(rl, qlr.h[e], d0);             // fp16 x fp16 products are exact in fp32 (FHFMA): same sums
+              d0 = fhfma_hi(rl, qlr.h[e], d0);             // as fmaf(float(q), float(k), d) without the conversions
+              d1 = fhfma_lo(rh, qhr.h[e], d1);
+              d1 = fhfma_hi(rh, qhr.h[e], d1);
+            }
+            d[ps] = d0 + d1;
+          }
+          // the RoPE registers are free: fetch the rows of this warp's next tile of the segment under the rest of this one
+          if (k + WARPS < row_end) load_table((j + WARPS) * kTile, cs, sn);
+
+#pragma unroll
+          for (int o = 1; o <= 4; o <<= 1) {
+#pragma unroll
+            for (int ps = 0; ps < PASSES; ++ps) d[ps] += __shfl_xor_sync(0xffffffffu, d[ps], o);
+          }
+          // fp16 logit exactly as the reference forms it: fp16(matmul) / sqrt(D) -> fp16 (:111-113)
+          float sc[PASSES];
+          float mx = -CUDART_INF_F;
+#pragma unroll
+          for (int ps = 0; ps < PASSES; ++ps) {
+            const int tl = ps * 4 + g;
+            const bool valid = tl < ntok;
+            const __half s16 = __float2half_rn(div_by_const(__half2float(__float2half_rn(d[ps])), p.sqrt_d, p.rsqrt_d));
+            if (valid && c == 0 && lg) lg[tok0 + tl] = s16;
+            sc[ps] = valid ? __half2float(s16) : -CUDART_INF_F;
+            mx = fmaxf(mx, sc[ps]);
+          }
+          // online softmax (:135): m is warp-uniform; l and acc are per key group until the segment ends
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+          const float m_new = fmaxf(m, mx);
+          if (m_new > -CUDART_INF_F) {
+            if (m_new != m) {
+              const float corr = fast_exp2((m - m_new) * kLog2e);
+              lsum *= corr;
+#pragma unroll
+              for (int e = 0; e < E2; ++e) { accl[e] *= corr; acch[e] *= corr; }
+              m = m_new;
+            }
+            // the probabilities enter P.V as fp16, as in the reference (softmax(...).to(fp16) @ V, :135-138); the running
+            // sum uses the same rounded values, so the final normalisation is exact for what was accumulated
+            __half2 ph[PASSES];
+#pragma unroll
+            for (int ps = 0; ps < PASSES; ++ps) {
+              ph[ps] = __float2half2_rn(fast_exp2((sc[ps] - m) * kLog2e));
+              lsum += __low2float(ph[ps]);
+            }
+            // P.V (:138)
+#pragma unroll
+            for (int ps = 0; ps < PASSES; ++ps) {
+              const int tl = ps * 4 + g;
+              HV vl, vh;
+              *reinterpret_cast<Vec*>(&vl) = *reinterpret_cast<const Vec*>(Vs + tl * kRowBytes + c * VB);
+              *reinterpret_cast<Vec*>(&vh) = *reinterpret_cast<const Vec*>(Vs + tl * kRowBytes + D + c * VB);
+#pragma unroll
+              for (int e = 0; e < NH2; ++e) {
+                accl[2 * e] = fhfma_lo(vl.h[e], ph[ps], accl[2 * e]);
+                accl[2 * e + 1] = fhfma_hi(vl.h[e], ph[ps], accl[2 * e + 1]);
+                acch[2 * e] = fhfma_lo(vh.h[e], ph[ps], acch[2 * e]);
+                acch[2 * e + 1] = fhfma_hi(vh.h[e], ph[ps], acch[2 * e + 1]);
+              }
+            }
+          }
+
+          // stage s is free: refill it with this warp's tile STAGES ahead (possibly the next layer's)
+          if (generic_writes) fence_proxy_async();         // generic-proxy writes above vs the async-proxy copy below
+          __syncwarp();
+          issue_next(s);
+          s = (s + 1 == STAGES) ? 0 : s + 1;
+        }
+
+        STAMP(l, 3);                                       // tiles done
+        // ---- this warp's tiles of the segment are done: reduce-scatter over the 4 key groups (lane bits 3 and 4) -----
+        lsum += __shfl_xor_sync(0xffffffffu, lsum, 8);
+        lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
+        float keep[E2];
+        const bool up = (g & 1) != 0;                 // bit 3: keep the upper half-row, send the lower
+#pragma unroll
+        for (int e = 0; e < E2; ++e) {
+          const float send = up ? accl[e] : acch[e];
+          const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+          keep[e] = (up ? acch[e] : accl[e]) + recv;
+        }
+        const bool up2 = (g & 2) != 0;                // bit 4: keep the upper PER of the E2 values
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+          const float send = up2 ? keep[e] : keep[e + PER];
+          const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+          fin[e] = (up2 ? keep[e + PER] : keep[e]) + recv;
+        }
+      }
+
+      // ---- CTA level: every warp checks in at the segment's shared-memory buffer; the last one combines ------------
+      float* sb = segbuf + (seg_seq % step_seg_bufs(WARPS)) * kSegBufFloats;
+      float2* sml = reinterpret_cast<float2*>(sb + WARPS * D);
+      volatile unsigned* sctl = reinterpret_cast<volatile unsigned*>(sb + WARPS * D + WARPS * 2);   // [0] arrivals, [1] uses done
+      const unsigned use = seg_seq / step_seg_bufs(WARPS);
+      while (sctl[1] != use) __nanosleep(40);                 // the buffer's previous segment has been combined
+      if (have) {
+        const int d0 = (g & 1) * (D / 2) + c * E2 + (g >> 1) * PER;   // first of the PER dims this lane owns
+        *reinterpret_cast<PV_t*>(sb + warp * D + d0) = *reinterpret_cast<const PV_t*>(fin);
+      }
+      if (lane == 0) sml[warp] = make_float2(m, lsum);
+      __syncwarp();
+      unsigned arrived = 0;
+      if (lane == 0) {
+        __threadfence_block();
+        arrived = atomicAdd(const_cast<unsigned*>(&sctl[0]), 1u);
+      }
+      arrived = __shfl_sync(0xffffffffu, arrived, 0);
+      if (arrived != WARPS - 1) continue;
+      __threadfence_block();
+      STAMP(l, 4);                                         // last of the CTA: combining
+
+      // last warp of the CTA at this segment: combine the WARPS partials on chip
+      float M, Lsum;
+      float o[PER];
+      {
+        const float2 mlj = lane < WARPS ? sml[lane] : make_float2(-CUDART_INF_F, 0.f);
+        M = warp_max(mlj.x);
+        const float wj = (M > -CUDART_INF_F && lane < WARPS) ? fast_exp2((mlj.x - M) * kLog2e) : 0.f;
+        Lsum = warp_sum(mlj.y * wj);
+#pragma unroll
+        for (int e = 0; e < PER; ++e) o[e] = 0.f;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+          const float ww = __shfl_sync(0xffffffffu, wj, w);
+          if (ww > 0.f) {                                      // warps without a tile in the segment wrote no partial
+            const PV_t v = *reinterpret_cast<const PV_t*>(sb + w * D + lane * PER);
+            const float* vf = reinterpret_cast<const float*>(&v);
+#pragma unroll
+            for (int e = 0; e < PER; ++e) o[e] = fmaf(vf[e], ww, o[e]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        sctl[0] = 0;
+        __threadfence_block();
+        sctl[1] = use + 1;                                     // hand the buffer to segment seg_seq + step_seg_bufs(WARPS)
+      }
+
+      // ---- global level: the CTAs whose ranges intersect row i --------------------------------------------------------
+      const unsigned tf = static_cast<unsigned>(i) * p.tpr;
+      const int o_first = static_cast<int>(((tf + 1) * R.geff - 1) / R.T);
+      const int o_last = static_cast<int>(((tf + p.tpr) * R.geff - 1) / R.T);
+      const int n_grp = o_last - o_first + 1;
+      if (n_grp == 1) {
+        emit_row(l, row, o, Lsum > 0.f ? 1.f / Lsum : 0.f, M);
+        continue;
+      }
+      {
+        const int64_t slot = static_cast<int64_t>(l) * p.slots + R.vcta + i;
+        *reinterpret_cast<PV_t*>(p.part + slot * D + lane * PER) = *reinterpret_cast<const PV_t*>(o);
+        if (lane == 0) p.part_ml[slot] = make_float2(M, Lsum);
+      }
+      __syncwarp();
+      unsigned prev = 0;
+      unsigned int* ticket = p.tickets + static_cast<int64_t>(l) * p.rows + row;
+      if (lane == 0) {
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");     // release: the partial is visible device-wide
+        prev = atomicAdd(ticket, 1u);
+      }
+      prev = __shfl_sync(0xffffffffu, prev, 0);
+      STAMP(l, 5);                                         // CTA partial published, ticket taken
+      if (prev != static_cast<unsigned>(n_grp - 1)) continue;
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");       // acquire side
+
+      // last CTA of the row: merge its n_grp partials (a handful: rows / CTAs)
+      {
+        const int64_t base = static_cast<int64_t>(l) * p.slots + o_first + i;
+        const float* rec = p.part + base * D + lane * PER;
+        const float2* ml = p.part_ml + base;
+        float Mg = -CUDART_INF_F, Lp = 0.f;
+        float og[PER];
+#pragma unroll
+        for (int e = 0; e < PER; ++e) og[e] = 0.f;
+        constexpr int kU = 8;                              // partial loads in flight per lane
+#pragma unroll 1
+        for (int c0 = 0; c0 < n_grp; c0 += kU) {
+          const int nc = min(kU, n_grp - c0);
+          const float2 mlj = lane < nc ? __ldcg(ml + c0 + lane) : make_float2(-CUDART_INF_F, 0.f);
+          PV_t vv[kU];
+#pragma unroll
+          for (int u = 0; u < kU; ++u)
+            vv[u] = __ldcg(reinterpret_cast<const PV_t*>(rec + static_cast<int64_t>(c0 + min(u, nc - 1)) * D));
+          const float Mn = fmaxf(Mg, warp_max(mlj.x));
+          const float corr = (Mn > -CUDART_INF_F) ? fast_exp2((Mg - Mn) * kLog2e) : 0.f;   // Mg = -inf -> 0
+          const float wj = (Mn > -CUDART_INF_F) ? fast_exp2((mlj.x - Mn) * kLog2e) : 0.f;
+          Lp = fmaf(mlj.y, wj, Lp * corr);
+#pragma unroll
+          for (int e = 0; e < PER; ++e) og[e] *= corr;
+          Mg = Mn;
 #pragma unroll
           for (int u = 0; u < kU; ++u) {
-            const float w = __shfl_sync(0xffffffffu, wj, (u0 + u) & 31);
-            const float wu = (u0 + u < nc) ? w : 0.f;
+            const float w = __shfl_sync(0xffffffffu, wj, u);
+            const float wu = (u < nc) ? w : 0.f;
             const float* vf = reinterpret_cast<const float*>(&vv[u]);
 #pragma unroll
-            for (int k = 0; k < PER; ++k) o[k] = fmaf(vf[k], wu, o[k]);
+            for (int e = 0; e < PER; ++e) og[e] = fmaf(vf[e], wu, og[e]);
           }
         }
+        const float Lg = warp_sum(Lp);
+        if (lane == 0) *ticket = 0;                        // self-cleaning ticket for the next step
+        STAMP(l, 6);                                       // row merged
+        emit_row(l, row, og, Lg > 0.f ? 1.f / Lg : 0.f, Mg);
+        STAMP(l, 7);                                       // row stored and signalled
       }
-      const float Lsum = warp_sum(Lp);
-      if (lane == 0) *ticket = 0;                        // self-cleaning ticket for the next step
-      emit_row(seg_l, seg_row, lane * PER, o, Lsum > 0.f ? 1.f / Lsum : 0.f, M);
     }
   }
 
@@ -640,17 +727,22 @@ __global__ void __launch_bounds__(WARPS * 32, 1) decode_step_kernel(const StepPa
       atomicAdd(p.ctrl, 1u);                             // steps completed: the next launch's epoch
     }
   }
+#undef STAMP
 }
 
 template <int D, int WARPS, int STAGES, int PASSES>
 constexpr size_t step_smem_bytes() {
   return static_cast<size_t>(WARPS) * STAGES * 2 * (4 * PASSES) * D * 2 + WARPS * STAGES * 8 +
+         static_cast<size_t>(step_seg_bufs(WARPS)) * (WARPS * D + WARPS * 2 + 4) * sizeof(float) +
          kStepSmemLayers * sizeof(SpattenStepLayer);
 }
 
 // Kernel variants: (warps per CTA, ring stages per warp).  192 KiB of K/V ring per SM either way.
 //   0: 8 warps x 3 stages x 16-token tiles     1: 16 warps x 3 stages x 8-token tiles (4 warps per scheduler, <= 128 regs)
-constexpr int kStepVariants = 2;
+//   2: 12 warps x 2 stages x 16-token tiles   3: 12 warps x 4 stages x 8-token tiles
+//   4: 8 x 2 x 16 tok   5: 8 x 2 x 8 tok   6: 16 x 2 x 8 tok   7: 8 x 4 x 8 tok  (shallower rings: less queueing in front of
+//   the latency-critical query / flag loads)
+constexpr int kStepVariants = 9;
 constexpr int kStepMaxWarps = 16;
 using StepKernel = void (*)(const StepParams);
 struct StepVariant {
@@ -661,15 +753,27 @@ struct StepVariant {
 template <int D>
 static StepVariant step_variant(int v) {
   if (v == 1) return {decode_step_kernel<D, 16, 3, 2>, 16, 8, step_smem_bytes<D, 16, 3, 2>()};
+  if (v == 2) return {decode_step_kernel<D, 12, 2, 4>, 12, 16, step_smem_bytes<D, 12, 2, 4>()};
+  if (v == 3) return {decode_step_kernel<D, 12, 4, 2>, 12, 8, step_smem_bytes<D, 12, 4, 2>()};
+  if (v == 4) return {decode_step_kernel<D, 8, 2, 4>, 8, 16, step_smem_bytes<D, 8, 2, 4>()};
+  if (v == 5) return {decode_step_kernel<D, 8, 2, 2>, 8, 8, step_smem_bytes<D, 8, 2, 2>()};
+  if (v == 6) return {decode_step_kernel<D, 16, 2, 2>, 16, 8, step_smem_bytes<D, 16, 2, 2>()};
+  if (v == 7) return {decode_step_kernel<D, 8, 4, 2>, 8, 8, step_smem_bytes<D, 8, 4, 2>()};
+  if (v == 8) return {decode_step_kernel<D, 8, 3, 4, true>, 8, 16, step_smem_bytes<D, 8, 3, 4>()};   // timeline build
   return {decode_step_kernel<D, 8, 3, 4>, 8, 16, step_smem_bytes<D, 8, 3, 4>()};
 }
-static int step_variant_choice() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SPATTEN_STEP_VARIANT");      // tuning knob for tools/microbench.py; default 0
-    v = (e && e[0] == '1') ? 1 : 0;
+// Measured on B200 (profiles/r2_step_variants.jsonl): with few tiles per warp and layer (BASELINE config 2: 27.7
+// tiles per SM) twelve warps hide the segment-boundary latencies better (8.6 vs 9.2 us per layer); long rows stream
+// best from eight warps with two-stage rings (0.97 of the measured HBM peak at b=8, H=5, n=16384).
+// SPATTEN_STEP_VARIANT=<n> overrides the choice (tools/microbench.py).
+static int step_variant_choice(long tiles_per_layer, int sms) {
+  static int forced = -2;
+  if (forced == -2) {
+    const char* e = getenv("SPATTEN_STEP_VARIANT");
+    forced = (e && e[0] >= '0' && e[0] < '0' + kStepVariants) ? e[0] - '0' : -1;
   }
-  return v;
+  if (forced >= 0) return forced;
+  return tiles_per_layer >= 64L * sms ? 4 : 2;
 }
 
 template <int D>
@@ -713,6 +817,11 @@ static StepWorkspace step_workspace(int L, int rows, int D, int W) {
 
 using namespace spatten;
 
+static unsigned long long* g_step_dbg = nullptr;
+// Debug hook (not part of the public header): device buffer [L][grid][warps][8] u64 for %globaltimer stamps; selects
+// the instrumented build of the kernel while set.
+extern "C" void spatten_debug_set_step_timeline(unsigned long long* dev_buf) { g_step_dbg = dev_buf; }
+
 extern "C" size_t spatten_decode_step_workspace_bytes(int32_t num_layers, int32_t batch, int32_t num_heads, int32_t head_dim) {
   if (num_layers <= 0 || batch <= 0 || num_heads <= 0 || (head_dim != 64 && head_dim != 128)) return 0;
   const int sms = sm_count();
@@ -753,7 +862,10 @@ extern "C" int spatten_decode_step(const SpattenStepArgs* a, void* stream) {
   SPATTEN_CHECK_ARG(a->n_peers >= 0 && a->n_peers <= kStepMaxPeers, "spatten_decode_step: bad n_peers");
 
   int grid = 0;
-  const int variant = step_variant_choice();
+  const long tiles16 = static_cast<long>(a->batch) * a->num_heads * ((n_total + 15) / 16);
+  const int sms_now = sm_count();
+  if (sms_now <= 0) return SPATTEN_ERR_CUDA;
+  const int variant = g_step_dbg ? 8 : step_variant_choice(tiles16, sms_now);
   if (int rc = (a->head_dim == 128 ? step_grid<128>(variant, grid) : step_grid<64>(variant, grid))) return rc;
   const StepVariant sv = a->head_dim == 128 ? step_variant<128>(variant) : step_variant<64>(variant);
 
@@ -781,6 +893,7 @@ extern "C" int spatten_decode_step(const SpattenStepArgs* a, void* stream) {
   p.rows = static_cast<unsigned>(a->batch) * a->num_heads;
   p.sqrt_d = static_cast<float>(sqrt(static_cast<double>(a->head_dim)));
   p.rsqrt_d = 1.0f / p.sqrt_d;
+  p.dbg = g_step_dbg;
 
   SPATTEN_CHECK_ARG(static_cast<double>(p.rows) * p.tpr * p.W < 4.0e9,
                     "spatten_decode_step: batch * heads * tiles too large for the 32-bit work-list arithmetic");

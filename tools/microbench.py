@@ -76,6 +76,47 @@ def bench_step(b, H, D, n, L, iters, chain=True, logits_on=True):
             "frac_6445": round(bytes_layer / us_layer / 1e3 / 6445, 4), "timed_out": step.timed_out()}
 
 
+def step_timeline(b, H, D, n, L, chain=True):
+    """Per-layer phase timeline of the persistent step kernel (instrumented build), medians over CTAs, ns."""
+    import ctypes as C
+    import numpy as np
+    from spatten_b200 import _lib
+    lib = _lib.load()
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(1)
+    kc = [torch.randn((b, H, n + 8, D), generator=g, device=dev, dtype=torch.float16) for _ in range(L)]
+    vc = [torch.randn((b, H, n + 8, D), generator=g, device=dev, dtype=torch.float16) for _ in range(L)]
+    q = torch.randn((L, b, H, D), generator=g, device=dev, dtype=torch.float16)
+    rope = ops.rope_table(D, n + 8, dev)
+    logits = torch.empty((L, b, H, n + 8), device=dev, dtype=torch.float16)
+    step = ops.DecodeStep(q, kc, vc, n - 1, rope, k_new=q, v_new=q, logits=logits, chain=chain)
+    for _ in range(3):
+        step.launch()
+    torch.cuda.synchronize()
+    G, Wp = torch.cuda.get_device_properties(0).multi_processor_count, 8
+    buf = torch.zeros(L * G * Wp * 8, dtype=torch.int64, device=dev)
+    lib.spatten_debug_set_step_timeline(C.c_void_p(buf.data_ptr()))
+    step.launch()
+    torch.cuda.synchronize()
+    lib.spatten_debug_set_step_timeline(None)
+    t = buf.cpu().numpy().reshape(L, G, Wp, 8).astype(np.float64)
+    t[t == 0] = np.nan
+    t0 = np.nanmin(t)
+    names = ["seg_reached", "prev_layer_seen", "first_tile+q", "tiles_done", "cta_last_arrived", "ticket_taken", "row_merged",
+             "row_signalled"]
+    print(f"step timeline b={b} H={H} n={n} L={L} chain={chain}: total {(np.nanmax(t) - t0) / 1e3:.1f} us")
+    lay_end = np.array([np.nanmax(t[l, :, :, 7]) if np.isfinite(t[l, :, :, 7]).any() else np.nanmax(t[l]) for l in range(L)])
+    print("  layer period (last row signalled), us: median %.2f" % np.median(np.diff(lay_end) / 1e3))
+    for l in (L // 2, L // 2 + 1):
+        base = lay_end[l - 1]
+        print(f"  layer {l}: ns after layer {l-1}'s last row was signalled (min / median / max over warps)")
+        for k, nm in enumerate(names):
+            v = t[l, :, :, k].ravel()
+            v = v[np.isfinite(v)] - base
+            if v.size:
+                print(f"    {nm:18s} {np.min(v):8.0f} {np.median(v):8.0f} {np.max(v):8.0f}   (n={v.size})")
+
+
 def _time_graph(fn, iters):
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
@@ -222,7 +263,11 @@ if __name__ == "__main__":
     ap.add_argument("--prefill", action="store_true", help="tcgen05 prefill attention timings")
     ap.add_argument("--step", action="store_true", help="persistent decode-step kernel timings")
     ap.add_argument("--no-chain", action="store_true")
+    ap.add_argument("--step-timeline", action="store_true")
     a = ap.parse_args()
+    if a.step_timeline:
+        step_timeline(*map(int, (a.shape or "1,32,128,2048,32").split(",")), chain=not a.no_chain)
+        sys.exit(0)
     if a.step:
         if a.shape:
             shapes = [tuple(map(int, a.shape.split(",")))]
