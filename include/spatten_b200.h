@@ -217,6 +217,11 @@ typedef struct SpattenStepArgs {
 } SpattenStepArgs;
 size_t spatten_decode_step_workspace_bytes(int32_t num_layers, int32_t batch, int32_t num_heads, int32_t head_dim);
 int spatten_decode_step(const SpattenStepArgs* args, void* stream);
+/* The step with HOST buffers: `in_host` (pinned) holds every layer's q | k_new | v_new exactly as the device region
+ * `in_dev` that the layer descriptors point into; one host->device copy, the launch, one device->host copy of
+ * `out_bytes` from `out_dev` (every layer's output) to `out_host`, stream synchronised before returning. */
+int spatten_decode_step_host(const SpattenStepArgs* args, const void* in_host, void* in_dev, size_t in_bytes,
+                             const void* out_dev, void* out_host, size_t out_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Prefill attention (q_len > 1) on the tcgen05 tensor cores.  Same reference lines as spatten_decode_attn

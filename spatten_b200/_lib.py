@@ -191,6 +191,8 @@ def _bind_optional(lib):
     lib.spatten_decode_step_workspace_bytes.restype = C.c_size_t
     lib.spatten_decode_step_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     lib.spatten_decode_step.argtypes = [C.POINTER(StepArgs), C.c_void_p]
+    lib.spatten_decode_step_host.argtypes = [C.POINTER(StepArgs), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                             C.c_size_t, C.c_void_p]
 
 
 def check(code: int):

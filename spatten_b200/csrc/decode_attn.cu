@@ -1007,9 +1007,14 @@ extern "C" int spatten_decode_attn_host(const SpattenDecodeArgs* a, const void* 
   const int q_len = a->q_len > 1 ? a->q_len : 1;
   const size_t qb = static_cast<size_t>(a->batch) * q_len * a->num_heads * a->head_dim * sizeof(__half);
   const size_t kb = static_cast<size_t>(a->batch) * a->num_kv_heads * a->head_dim * sizeof(__half);
-  cudaError_t e = cudaMemcpyAsync(const_cast<void*>(a->q), q_host, qb, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess && a->append) e = cudaMemcpyAsync(const_cast<void*>(a->k_new), k_new_host, kb, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess && a->append) e = cudaMemcpyAsync(const_cast<void*>(a->v_new), v_new_host, kb, cudaMemcpyHostToDevice, st);
+  // one packed copy when the caller laid q | k_new | v_new out back to back on both sides (saves two driver calls)
+  const uint8_t* qh8 = static_cast<const uint8_t*>(q_host);
+  const uint8_t* qd8 = static_cast<const uint8_t*>(a->q);
+  const bool packed = a->append && k_new_host == qh8 + qb && v_new_host == qh8 + qb + kb &&
+                      a->k_new == qd8 + qb && a->v_new == qd8 + qb + kb;
+  cudaError_t e = cudaMemcpyAsync(const_cast<void*>(a->q), q_host, packed ? qb + 2 * kb : qb, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && a->append && !packed) e = cudaMemcpyAsync(const_cast<void*>(a->k_new), k_new_host, kb, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && a->append && !packed) e = cudaMemcpyAsync(const_cast<void*>(a->v_new), v_new_host, kb, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return cuda_fail(e, "spatten_decode_attn_host: H2D copy");
   const int rc = spatten_decode_attn(a, stream);
   if (rc != SPATTEN_OK) return rc;

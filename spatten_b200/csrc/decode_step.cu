@@ -716,7 +716,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) decode_step_kernel(const StepPa
   }
 
   // ---- step epilogue ------------------------------------------------------------------------------------------------
-  if (p.final_wait && blockIdx.x == 0 && warp == 0) wait_layer(p.L - 1);
+  // head sharding: the launch completes only when every rank's rows of every layer are in the local gather buffer
+  // (chained steps have already waited for all layers but the last)
+  if (p.final_wait && blockIdx.x == 0 && warp == 0) {
+#pragma unroll 1
+    for (int l = p.chain ? p.L - 1 : 0; l < p.L; ++l) wait_layer(l);
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -942,5 +947,23 @@ extern "C" int spatten_decode_step(const SpattenStepArgs* a, void* stream) {
   cfg.stream = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaLaunchKernelEx(&cfg, sv.kernel, p);
   if (e != cudaSuccess) return cuda_fail(e, "decode_step_kernel launch");
+  return SPATTEN_OK;
+}
+
+// The step with HOST buffers for the per-step tensors: one packed host -> device copy of every layer's q | k_new | v_new
+// (the caller lays them out so that `in_dev` is what the layer descriptors point into), the persistent launch, one
+// device -> host copy of every layer's output, stream synchronised before returning.
+extern "C" int spatten_decode_step_host(const SpattenStepArgs* a, const void* in_host, void* in_dev, size_t in_bytes,
+                                        const void* out_dev, void* out_host, size_t out_bytes, void* stream) {
+  SPATTEN_CHECK_ARG(a != nullptr && in_host && in_dev && out_dev && out_host && in_bytes > 0 && out_bytes > 0,
+                    "spatten_decode_step_host: NULL argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemcpyAsync(in_dev, in_host, in_bytes, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return cuda_fail(e, "spatten_decode_step_host: H2D copy");
+  const int rc = spatten_decode_step(a, stream);
+  if (rc != SPATTEN_OK) return rc;
+  e = cudaMemcpyAsync(out_host, out_dev, out_bytes, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cuda_fail(e, "spatten_decode_step_host: D2H copy / sync");
   return SPATTEN_OK;
 }

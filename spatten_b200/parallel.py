@@ -124,3 +124,50 @@ class PeerExchange:
 
     def timed_out(self) -> bool:
         return bool(self.timeout.item())
+
+
+class PeerStepExchange:
+    """Fused output exchange for the persistent decode-step kernel (`spatten_decode_step`, ops.DecodeStep).
+
+    Same symmetric-memory layout as `PeerExchange` -- gather buffers fp16 [L, N, b, H/N, D] and one u32 flag per
+    (layer, producing rank) -- but the flags count ROWS: every finished (sequence, head) row is stored into all N
+    peers' buffers by a whole warp and lanes 0..N-1 each add 1 to one peer's flag word (release at system scope), so
+    there is no grid-wide completion counter on the critical path.  A consumer knows layer l of step s is complete
+    when flags[l, r] == rows_per_rank * s for every r.  With `chain=True` the kernel itself waits for layer l's flags
+    before it reads layer l+1's query; in every mode it waits for all layers before the launch completes.
+    """
+
+    def __init__(self, step, shard: HeadShard, group=None):
+        import torch.distributed._symmetric_memory as symm
+        a = step.args
+        L, b, hl, D = a.num_layers, a.batch, a.num_heads, a.head_dim
+        if hl != shard.count:
+            raise ValueError("PeerStepExchange: the step must be built over this rank's heads only")
+        n = shard.world
+        self.shard, self.layers = shard, L
+        self.slot_elems = b * hl * D
+        out_bytes = L * n * self.slot_elems * 2
+        self.flag_off = (out_bytes + 255) // 256 * 256
+        total = self.flag_off + L * n * 4
+        self.buf = symm.empty(total, dtype=torch.uint8, device=step.device)
+        self.buf.zero_()
+        group = group if group is not None else dist.group.WORLD
+        self.hdl = symm.rendezvous(self.buf, group)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.gathered = self.buf[:out_bytes].view(torch.float16).view(L, n, b, hl, D)
+        self.flags = self.buf[self.flag_off:self.flag_off + L * n * 4].view(torch.int32).view(L, n)
+        r = shard.rank
+        a.n_peers = n
+        for p in range(n):
+            a.peer_out[p] = self.ptrs[p] + r * self.slot_elems * 2            # layer 0, slot `rank` in rank p's buffer
+            a.peer_flags[p] = self.ptrs[p] + self.flag_off + r * 4            # flag [0, rank] in rank p's memory
+        a.peer_layer_stride = n * self.slot_elems
+        a.peer_flag_layer_stride = n
+        a.wait_flags = self.flags.data_ptr()
+        self.step = step
+        torch.cuda.synchronize(step.device)
+        dist.barrier(group=group)
+
+    def heads(self, layer: int) -> torch.Tensor:
+        """[b, H, D] of `layer` in global head order (valid once the step's launch has completed)."""
+        return gathered_to_heads(self.gathered[layer])

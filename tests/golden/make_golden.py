@@ -20,6 +20,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))           # tests/
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))   # repo root (baseline/)
 sys.path.insert(0, "/root/reference")
 
 from spatten_llm.pos_shift.modify_llama import llama_pos_shift_attention_forward  # noqa: E402
@@ -29,60 +30,11 @@ from cases import (CHAIN_CASES, FWD_CASES, PRUNE_CASES, build_chain_inputs, buil
                    build_prune_inputs)
 
 
-class Rotary433(torch.nn.Module):
-    """transformers 4.33 LlamaRotaryEmbedding (restated; its source is not on disk)."""
-
-    def __init__(self, dim, max_position_embeddings=2048, base=10000):
-        super().__init__()
-        self.dim, self.base = dim, base
-        inv_freq = 1.0 / (base ** (torch.arange(0, dim, 2).float() / dim))
-        self.register_buffer("inv_freq", inv_freq, persistent=False)
-        self._set(max_position_embeddings)
-
-    def _set(self, seq_len):
-        self.max_seq_len_cached = seq_len
-        t = torch.arange(seq_len, dtype=self.inv_freq.dtype)
-        freqs = torch.einsum("i,j->ij", t, self.inv_freq)
-        emb = torch.cat((freqs, freqs), dim=-1)
-        self.cos_cached = emb.cos()[None, None, :, :].to(torch.float32)
-        self.sin_cached = emb.sin()[None, None, :, :].to(torch.float32)
-
-    def forward(self, x, seq_len=None):
-        if seq_len > self.max_seq_len_cached:
-            self._set(seq_len)
-        return (self.cos_cached[:, :, :seq_len, ...].to(dtype=x.dtype),
-                self.sin_cached[:, :, :seq_len, ...].to(dtype=x.dtype))
+from baseline.ref_shim import Const, Linear, Rotary433, ShimAttention as _ShimBase     # noqa: E402
 
 
-class Const(torch.nn.Module):
-    """Stands in for a projection when the case is specified after the projections."""
-
-    def __init__(self, value):
-        super().__init__()
-        self.value = value
-
-    def forward(self, _):
-        return self.value
-
-
-class Linear(torch.nn.Module):
-    def __init__(self, w):
-        super().__init__()
-        self.weight = w
-
-    def forward(self, x):
-        return torch.nn.functional.linear(x, self.weight)
-
-
-class ShimAttention(torch.nn.Module):
+class ShimAttention(_ShimBase):
     forward = llama_pos_shift_attention_forward          # the reference function, unmodified
-
-    def __init__(self, H, H_kv, D):
-        super().__init__()
-        self.config = types.SimpleNamespace(pretraining_tp=1)
-        self.hidden_size, self.num_heads, self.num_key_value_heads = H * D, H, H_kv
-        self.head_dim, self.num_key_value_groups = D, H // H_kv
-        self.rotary_emb = Rotary433(D)
 
 
 def run_fwd(c):

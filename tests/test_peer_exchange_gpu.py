@@ -25,3 +25,4 @@ def test_fused_exchange_two_gpus(fold_wait):
                        env=env, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("fused exchange OK") == 2
+    assert r.stdout.count("step exchange OK") == 2

@@ -70,6 +70,42 @@ for step in range(4):
             print(f"[r{rank}] step {step} layer {l}: mismatch, max abs {float((got.float() - full[l].float()).abs().max())}", flush=True)
     dist.barrier()
 print(f"[r{rank}] fused exchange {'OK' if ok and not px.timed_out() else 'FAILED'} timed_out={px.timed_out()}", flush=True)
+
+# ---- the persistent decode-step kernel with the exchange fused in: chained and independent-layer modes ----------------
+from spatten_b200.parallel import PeerStepExchange
+ok_step = True
+for chain in (True, False):
+    kcs2 = [kc[l][:, s].contiguous() for l in range(L)]
+    vcs2 = [vc[l][:, s].contiguous() for l in range(L)]
+    step = ops.DecodeStep(q[:, :, s].contiguous(), kcs2, vcs2, n, rope, k_new=kn[:, :, s].contiguous(),
+                          v_new=vn[:, :, s].contiguous(), chain=chain)
+    pxs = PeerStepExchange(step, sh)
+    # this rank's heads through the same step kernel without the exchange: the bit-exact reference for every slot
+    local = ops.DecodeStep(q[:, :, s].contiguous(), [k.clone() for k in kcs2], [v.clone() for v in vcs2], n, rope,
+                           k_new=kn[:, :, s].contiguous(), v_new=vn[:, :, s].contiguous(), chain=chain)
+    mine = local.launch().clone()
+    torch.cuda.synchronize()
+    every = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(every, mine)
+    for it in range(3):
+        pxs.gathered.zero_()
+        torch.cuda.synchronize()
+        dist.barrier()
+        step.launch()
+        torch.cuda.synchronize()
+        dist.barrier()
+        for l in range(L):
+            for r in range(world):
+                if not torch.equal(pxs.gathered[l, r], every[r][l]):
+                    ok_step = False
+                    print(f"[r{rank}] step chain={chain} it {it} layer {l} slot {r}: mismatch", flush=True)
+            rel = float((pxs.heads(l).float() - whole[l].float()).abs().max() / whole[l].float().abs().max())
+            if rel > 1e-3:
+                ok_step = False
+                print(f"[r{rank}] step chain={chain} layer {l}: differs from the unsharded launch by {rel}", flush=True)
+    if step.timed_out():
+        ok_step = False
+print(f"[r{rank}] step exchange {'OK' if ok_step else 'FAILED'}", flush=True)
 torch.cuda.synchronize()
 dist.barrier()
-os._exit(0 if ok else 1)
+os._exit(0 if (ok and ok_step) else 1)
