@@ -80,6 +80,8 @@ def test_decode_matches_reference_golden(c):
     (1, 12, 12, 64, 64),
     (1, 7, 7, 128, 15),
     (1, 32, 8, 128, 1000),       # GQA
+    (8, 5, 5, 128, 16383),       # BASELINE config 5, one GPU's shard at full size
+    (1, 40, 40, 128, 2047),      # 13B head count at the config-2 length
 ])
 def test_decode_matches_oracle(b, H, H_kv, D, past):
     seed = 9000 + b * 131 + H * 17 + past

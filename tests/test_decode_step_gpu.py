@@ -57,11 +57,13 @@ def oracle_layers(P, past, append=True):
     (2, 1, 7, 7, 128, 15),
     (2, 1, 32, 8, 128, 1000),      # GQA
     (1, 1, 2, 2, 128, 40000),      # more tiles per row than warps in the grid can hold as single tiles
+    (1, 8, 5, 5, 128, 16383),      # BASELINE config 5, one GPU's shard at full size (13B: 40 heads / 8 GPUs)
+    (1, 1, 40, 40, 128, 2047),     # 13B head count, config-2 length
 ])
 @pytest.mark.parametrize("chain", [True, False])
 def test_step_matches_oracle_and_per_layer_kernel(L, b, H, H_kv, D, past, chain):
     from spatten_b200 import ops
-    if past >= 40000 and not chain:
+    if past >= 16000 and not chain:
         pytest.skip("large case runs once")
     seed = 12000 + L * 7 + b * 131 + H * 17 + past
     P = make_problem(L, b, H, H_kv, D, past, seed)
@@ -76,7 +78,7 @@ def test_step_matches_oracle_and_per_layer_kernel(L, b, H, H_kv, D, past, chain)
     out = step.launch()
     torch.cuda.synchronize()
     assert not step.timed_out() and step.steps_completed() == 1
-    if past <= 4096:
+    if past <= 4096 or (b, H) == (8, 5):
         ref_out, ref_scores = oracle_layers(P, past)
         assert_logits_close(logits[..., :n].cpu(), ref_scores)
         assert rel_err(out.cpu(), ref_out) <= OUT_REL_TOL

@@ -62,3 +62,28 @@ def test_prefill_umma_matches_oracle_and_rowwise(b, H, H_kv, past, q_len):
     out2 = ops.decode_attn(q4, kc, vc, kv, rope, q_pos=pos.to(dev), mask=mask[:, 0].contiguous().to(dev), logits=lg2)
     assert (logits == lg2).float().mean().item() > 0.99
     assert rel_err(out.cpu(), out2.cpu()) <= 2e-3
+
+
+def test_prefill_umma_full_size_8192_sampled_rows_vs_oracle():
+    """BASELINE config 3's prefill length (S = 8192): sampled query rows of the tcgen05 path against the oracle's op
+    sequence (RoPE in fp16, fp16 logits = fp16(q.k)/sqrt(D), additive causal mask, fp32 softmax -> fp16, P.V)."""
+    import math
+    from spatten_b200 import ops
+    b, H, D, S, dev = 1, 2, 128, 8192, "cuda"
+    q = det_normal((b, H, S, D), 7101, 1.0, torch.float16)
+    k = det_normal((b, H, S, D), 7102, 1.0, torch.float16)
+    v = det_normal((b, H, S, D), 7103, 1.0, torch.float16)
+    pos = torch.arange(S).unsqueeze(0)
+    mask = causal_mask(b, S, 0, torch.float16)
+    out, logits = ops.prefill_attn(q.transpose(1, 2).contiguous().to(dev), k.to(dev), v.to(dev), S, ops.rope_table(D, S, dev),
+                                   pos.to(dev), mask[:, 0].contiguous().to(dev))
+    torch.cuda.synchronize()
+    rows = torch.tensor([0, 1, 127, 128, 129, 1000, 4095, 4096, 4097, 6143, 8000, 8190, 8191])
+    cos, sin = O.rotary_tables(D, S, torch.float16)
+    q_rot = O.rope_single(q[:, :, rows], cos, sin, rows.unsqueeze(0))
+    k_rot = O.rope_single(k, cos, sin, torch.arange(S).unsqueeze(0))
+    ref_scores = torch.matmul(q_rot, k_rot.transpose(2, 3)) / math.sqrt(D)
+    assert_logits_close(logits[:, :, rows.to(dev)].cpu(), ref_scores, "prefill 8192")
+    probs = torch.softmax((ref_scores + mask[:, :, rows]).float(), dim=-1).to(torch.float16)
+    ref_out = torch.matmul(probs, v)                                          # [b, H, rows, D]
+    assert rel_err(out[:, rows.to(dev)].cpu(), ref_out.transpose(1, 2)) <= OUT_REL_TOL
