@@ -309,6 +309,28 @@ typedef struct SpattenGatherArgs {
 } SpattenGatherArgs;
 int spatten_kv_gather(const SpattenGatherArgs* args, void* stream);
 
+/* Every layer of a cache in two launches (the reference loops over layers in Python, :55-70): per-layer pointers come
+ * from a DEVICE array; all layers share shapes and strides.  keep_idx: [num_layers, num_heads, keep_stride].  Out of
+ * place (fresh destination buffers, as the reference's cat()). */
+typedef struct SpattenPruneLayer {
+  const void* score;      /* [num_heads, score_stride] importance of this layer (score_reduce output, or attn_scores
+                             itself when batch == q_len == 1) */
+  const void* src_k;
+  const void* src_v;
+  void* dst_k;
+  void* dst_v;
+} SpattenPruneLayer;
+typedef struct SpattenPruneLayersArgs {
+  uint32_t struct_size;
+  int32_t num_layers, batch, num_heads, seq_len, num_coming, start, important, recent, score_dtype, row_bytes;
+  const SpattenPruneLayer* layers;          /* DEVICE pointer */
+  int64_t score_stride;                     /* elements */
+  int64_t src_stride_b, src_stride_h, dst_stride_b, dst_stride_h;   /* bytes */
+  int32_t* keep_idx;
+  int64_t keep_stride;
+} SpattenPruneLayersArgs;
+int spatten_prune_layers(const SpattenPruneLayersArgs* args, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * RTL-named stages that the reference Python never executes (README.md:11,21; "parity unpinned":
  * checked against the self-consistent restatements in oracle/spatten_oracle.py).

@@ -107,6 +107,18 @@ class GatherArgs(C.Structure):
     ]
 
 
+class PruneLayersArgs(C.Structure):
+    """Mirror of `SpattenPruneLayersArgs` (the per-layer table is a device array of 5 pointers per layer)."""
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("num_layers", C.c_int32), ("batch", C.c_int32), ("num_heads", C.c_int32),
+        ("seq_len", C.c_int32), ("num_coming", C.c_int32), ("start", C.c_int32), ("important", C.c_int32),
+        ("recent", C.c_int32), ("score_dtype", C.c_int32), ("row_bytes", C.c_int32),
+        ("layers", C.c_void_p), ("score_stride", C.c_int64),
+        ("src_stride_b", C.c_int64), ("src_stride_h", C.c_int64), ("dst_stride_b", C.c_int64), ("dst_stride_h", C.c_int64),
+        ("keep_idx", C.c_void_p), ("keep_stride", C.c_int64),
+    ]
+
+
 class SparsePvArgs(C.Structure):
     """Mirror of `SpattenSparsePvArgs`."""
     _fields_ = [
@@ -179,6 +191,7 @@ def _bind_optional(lib):
                                          C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
     lib.spatten_topk_select.argtypes = [C.POINTER(SelectArgs), C.c_void_p]
     lib.spatten_kv_gather.argtypes = [C.POINTER(GatherArgs), C.c_void_p]
+    lib.spatten_prune_layers.argtypes = [C.POINTER(PruneLayersArgs), C.c_void_p]
     lib.spatten_sparse_pv.argtypes = [C.POINTER(SparsePvArgs), C.c_void_p]
     lib.spatten_prefill_attn.argtypes = [C.POINTER(PrefillArgs), C.c_void_p]
     lib.spatten_wait_flags.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]

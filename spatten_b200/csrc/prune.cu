@@ -47,6 +47,8 @@ struct SelectParams {
   int32_t* keep;
   int64_t keep_stride;
   int seq_len, start, important, win_begin, win_end, tail_begin;
+  const SpattenPruneLayer* layers;   // optional (spatten_prune_layers): row r = head r % rows_per_layer of layer r / rows_per_layer
+  int rows_per_layer;
 };
 
 // One CTA per score row.  Radix select (8-bit digits, MSB first) finds the k-th largest key; a second,
@@ -60,7 +62,10 @@ __global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const SelectPa
   __shared__ unsigned s_wgt[kSelWarps], s_weq[kSelWarps];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const T* sc = static_cast<const T*>(p.score) + static_cast<int64_t>(blockIdx.x) * p.score_stride;
+  const T* sc = p.layers == nullptr
+                    ? static_cast<const T*>(p.score) + static_cast<int64_t>(blockIdx.x) * p.score_stride
+                    : static_cast<const T*>(p.layers[blockIdx.x / p.rows_per_layer].score) +
+                          static_cast<int64_t>(blockIdx.x % p.rows_per_layer) * p.score_stride;
   int32_t* keep = p.keep + static_cast<int64_t>(blockIdx.x) * p.keep_stride;
   const int n = p.win_end - p.win_begin;
   const int n_pad = (n + kSelThreads - 1) / kSelThreads * kSelThreads;
@@ -187,6 +192,7 @@ struct GatherParams {
   const int32_t* keep;
   int64_t keep_stride;
   int num_heads, keep_total, row_bytes, in_place;
+  const SpattenPruneLayer* layers;   // optional (spatten_prune_layers): blockIdx.z = layer
 };
 
 // grid.x = batch * heads * 2 (K then V); grid.y = row tiles (out of place) or 1 (in place: tiles are walked in
@@ -196,9 +202,17 @@ __global__ void __launch_bounds__(kGatherThreads) kv_gather_kernel(const GatherP
   const int which = blockIdx.x & 1;
   const int bh = blockIdx.x >> 1;
   const int h = bh % p.num_heads, b = bh / p.num_heads;
-  const uint8_t* src = (which ? p.src[1] : p.src[0]) + b * p.src_stride_b + h * p.src_stride_h;
-  uint8_t* dst = (which ? p.dst[1] : p.dst[0]) + b * p.dst_stride_b + h * p.dst_stride_h;
+  const uint8_t* src0 = which ? p.src[1] : p.src[0];
+  uint8_t* dst0 = which ? p.dst[1] : p.dst[0];
   const int32_t* keep = p.keep + h * p.keep_stride;
+  if (p.layers != nullptr) {
+    const SpattenPruneLayer& ly = p.layers[blockIdx.z];
+    src0 = static_cast<const uint8_t*>(which ? ly.src_v : ly.src_k);
+    dst0 = static_cast<uint8_t*>(which ? ly.dst_v : ly.dst_k);
+    keep += static_cast<int64_t>(blockIdx.z) * p.num_heads * p.keep_stride;
+  }
+  const uint8_t* src = src0 + b * p.src_stride_b + h * p.src_stride_h;
+  uint8_t* dst = dst0 + b * p.dst_stride_b + h * p.dst_stride_h;
   const int cpr = p.row_bytes >> 4;                       // 16-byte chunks per row
   const int chunks = kGatherTileRows * cpr;
   const int n_tiles = (p.keep_total + kGatherTileRows - 1) / kGatherTileRows;
@@ -261,7 +275,8 @@ extern "C" int spatten_topk_select(const SpattenSelectArgs* a, void* stream) {
   if (rc < 0) return rc;
   SPATTEN_CHECK_ARG(rc == 0, "spatten_topk_select: cache already fits (seq_len + num_coming <= cache size); nothing to select");
   SPATTEN_CHECK_ARG(a->score_stride >= a->seq_len && a->keep_stride >= keep_total, "spatten_topk_select: stride too small");
-  SelectParams p{a->score, a->score_stride, a->keep_idx, a->keep_stride, a->seq_len, a->start, a->important, wb, we, we};
+  SelectParams p{a->score, a->score_stride, a->keep_idx, a->keep_stride, a->seq_len, a->start, a->important, wb, we, we,
+                 nullptr, 1};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (a->score_dtype == SPATTEN_DTYPE_F16) topk_select_kernel<__half><<<a->num_rows, kSelThreads, 0, st>>>(p);
   else topk_select_kernel<float><<<a->num_rows, kSelThreads, 0, st>>>(p);
@@ -310,5 +325,45 @@ extern "C" int spatten_kv_gather(const SpattenGatherArgs* a, void* stream) {
   dim3 grid(a->batch * a->num_heads * 2, ipk ? 1 : std::min(n_tiles, 64));
   kv_gather_kernel<<<grid, kGatherThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
   cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? SPATTEN_OK : cuda_fail(e, "kv_gather_kernel launch");
+}
+
+// Every layer of a cache in two launches: one select over num_layers * num_heads score rows, one gather over
+// (layer, sequence, head, K|V, row tile) -- the Python loop over layers of the reference (kv_cache_token_pruning.py:55-70)
+// without per-layer launches, allocations or synchronisation.
+extern "C" int spatten_prune_layers(const SpattenPruneLayersArgs* a, void* stream) {
+  SPATTEN_CHECK_ARG(a != nullptr && a->struct_size == sizeof(SpattenPruneLayersArgs), "spatten_prune_layers: bad args/struct_size");
+  SPATTEN_CHECK_ARG(a->num_layers > 0 && a->batch > 0 && a->num_heads > 0 && a->layers && a->keep_idx,
+                    "spatten_prune_layers: bad shape or NULL pointer");
+  SPATTEN_CHECK_ARG(a->num_layers <= 65535, "spatten_prune_layers: too many layers");
+  SPATTEN_CHECK_ARG(a->score_dtype == SPATTEN_DTYPE_F16 || a->score_dtype == SPATTEN_DTYPE_F32,
+                    "spatten_prune_layers: score_dtype must be F16 or F32");
+  SPATTEN_CHECK_ARG(a->row_bytes > 0 && a->row_bytes % 16 == 0 && a->row_bytes <= 512,
+                    "spatten_prune_layers: row_bytes %d must be a multiple of 16 and <= 512", a->row_bytes);
+  SPATTEN_CHECK_ARG(((a->src_stride_b | a->src_stride_h | a->dst_stride_b | a->dst_stride_h) & 15) == 0,
+                    "spatten_prune_layers: byte strides must be multiples of 16");
+  int keep_total = 0, wb = 0, we = 0;
+  const int rc = spatten_prune_plan(a->seq_len, a->num_coming, a->start, a->important, a->recent, &keep_total, &wb, &we);
+  if (rc < 0) return rc;
+  SPATTEN_CHECK_ARG(rc == 0, "spatten_prune_layers: cache already fits; nothing to select");
+  SPATTEN_CHECK_ARG(a->score_stride >= a->seq_len && a->keep_stride >= keep_total, "spatten_prune_layers: stride too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SelectParams sp{nullptr, a->score_stride, a->keep_idx, a->keep_stride, a->seq_len, a->start, a->important, wb, we, we,
+                  a->layers, a->num_heads};
+  const int rows = a->num_layers * a->num_heads;
+  if (a->score_dtype == SPATTEN_DTYPE_F16) topk_select_kernel<__half><<<rows, kSelThreads, 0, st>>>(sp);
+  else topk_select_kernel<float><<<rows, kSelThreads, 0, st>>>(sp);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "topk_select_kernel launch");
+  GatherParams gp{};
+  gp.src_stride_b = a->src_stride_b; gp.src_stride_h = a->src_stride_h;
+  gp.dst_stride_b = a->dst_stride_b; gp.dst_stride_h = a->dst_stride_h;
+  gp.keep = a->keep_idx; gp.keep_stride = a->keep_stride;
+  gp.num_heads = a->num_heads; gp.keep_total = keep_total; gp.row_bytes = a->row_bytes; gp.in_place = 0;
+  gp.layers = a->layers;
+  const int n_tiles = (keep_total + kGatherTileRows - 1) / kGatherTileRows;
+  dim3 grid(a->batch * a->num_heads * 2, std::min(n_tiles, 64), a->num_layers);
+  kv_gather_kernel<<<grid, kGatherThreads, 0, st>>>(gp);
+  e = cudaGetLastError();
   return e == cudaSuccess ? SPATTEN_OK : cuda_fail(e, "kv_gather_kernel launch");
 }

@@ -42,18 +42,31 @@ class SpAttenKVCache:
         if plan is None:
             return past_key_values
         keep_total = plan[0]
-        self.importance_score = [ops.score_reduce(s) for s in attn_score_all]        # :51
-        self.keep_indices = []
-        out = []
-        for (k, v), score in zip(past_key_values, self.importance_score):
+        # :51 -- both sums run over singleton dims after a decode step (b = q = 1): an exact identity, no launch
+        self.importance_score = [s[0, :, 0, :] if (s.shape[0] == 1 and s.shape[2] == 1 and s.stride(3) == 1 and s.is_cuda)
+                                 else ops.score_reduce(s) for s in attn_score_all]
+        for (k, _), score in zip(past_key_values, self.importance_score):
             if score.shape[0] != k.shape[1]:
                 raise ValueError(f"score heads {score.shape[0]} != cache heads {k.shape[1]} "
                                  "(the reference's mask gather needs num_heads == num_key_value_heads)")
+        # room for the tokens the caller announced plus some slack, so decode appends in place
+        capacity = keep_total + int(num_coming) + 64
+        # all layers in two launches when they share shapes and strides (any HF cache does) ...
+        batched = ops.prune_layers(past_key_values, self.importance_score, seq_len, int(num_coming), self.start_size,
+                                   self.important_size, self.recent_size, capacity)
+        if batched is not None:
+            bufs, keep_idx = batched
+            self.keep_indices = list(keep_idx.unbind(0))
+            # fresh buffers of ours: the patched forward may append behind these views in place
+            return [[CacheBuffer(kb, keep_total).view(keep_total), CacheBuffer(vb, keep_total).view(keep_total)]
+                    for kb, vb in bufs]
+        # ... else layer by layer
+        self.keep_indices = []
+        out = []
+        for (k, v), score in zip(past_key_values, self.importance_score):
             keep = ops.topk_select(score, seq_len, int(num_coming), self.start_size, self.important_size,
                                    self.recent_size)
             self.keep_indices.append(keep)
-            # room for the tokens the caller announced plus some slack, so decode appends in place
-            k2, v2 = ops.kv_gather(k, v, keep, capacity=keep_total + int(num_coming) + 64)
-            # fresh buffers of ours: the patched forward may append behind these views in place
+            k2, v2 = ops.kv_gather(k, v, keep, capacity=capacity)
             out.append([CacheBuffer(k2._base, keep_total).view(keep_total), CacheBuffer(v2._base, keep_total).view(keep_total)])
         return out

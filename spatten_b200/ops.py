@@ -392,6 +392,51 @@ def kv_gather(k: torch.Tensor, v: torch.Tensor, keep_idx: torch.Tensor, k_out: O
     return k_out, v_out
 
 
+def prune_layers(past_key_values, scores, seq_len: int, num_coming: int, start: int, important: int, recent: int,
+                 capacity: int):
+    """All layers of a cache in two launches -- `spatten_prune_layers`.
+
+    past_key_values: list of (K, V) [b,H,S,D] with identical shapes, dtypes and strides; scores: list of [H, >=S] rows of
+    one dtype and row stride.  Returns (list of (K', V') capacity buffers [b,H,capacity,D] whose first keep_total rows are
+    the kept tokens, keep_idx int32 [L,H,keep_total]) or None when the layers are not uniform (caller falls back to the
+    per-layer calls).
+    """
+    lib = _lib.load()
+    L = len(past_key_values)
+    k0, v0 = past_key_values[0]
+    b, H, S, D = k0.shape
+    plan = prune_plan(seq_len, num_coming, start, important, recent)
+    keep_total = plan[0]
+    s0 = scores[0]
+    uniform = all(k.shape == k0.shape and v.shape == k0.shape and k.stride() == k0.stride() and v.stride() == k0.stride()
+                  and k.dtype == k0.dtype and v.dtype == k0.dtype and k.is_cuda and k.stride(3) == 1 and k.stride(2) == D
+                  for k, v in past_key_values) and \
+        all(s.dim() == 2 and s.shape[0] == H and s.dtype == s0.dtype and s.stride() == s0.stride() and s.stride(1) == 1
+            for s in scores)
+    es = k0.element_size()
+    if not uniform or (D * es) % 16 or D * es > 512:
+        return None
+    dev = k0.device
+    big = torch.empty((L, 2, b, H, capacity, D), dtype=k0.dtype, device=dev)
+    keep_idx = torch.empty((L, H, keep_total), dtype=torch.int32, device=dev)
+    dst0, dstep = big.data_ptr(), big.stride(0) * es
+    table_dev = torch.tensor([[s.data_ptr(), k.data_ptr(), v.data_ptr(), dst0 + l * dstep, dst0 + l * dstep + big.stride(1) * es]
+                              for l, ((k, v), s) in enumerate(zip(past_key_values, scores))], dtype=torch.int64).to(dev)
+    a = _lib.PruneLayersArgs()
+    a.struct_size = C.sizeof(_lib.PruneLayersArgs)
+    a.num_layers, a.batch, a.num_heads, a.seq_len = L, b, H, seq_len
+    a.num_coming, a.start, a.important, a.recent = num_coming, start, important, recent
+    a.score_dtype, a.row_bytes = _dtype_code(s0), D * es
+    a.layers, a.score_stride = table_dev.data_ptr(), s0.stride(0)
+    a.src_stride_b, a.src_stride_h = k0.stride(0) * es, k0.stride(1) * es
+    a.dst_stride_b, a.dst_stride_h = big.stride(2) * es, big.stride(3) * es
+    a.keep_idx, a.keep_stride = keep_idx.data_ptr(), keep_idx.stride(1)
+    with torch.cuda.device(dev):
+        _lib.check(lib.spatten_prune_layers(C.byref(a), C.c_void_p(_stream_ptr(dev))))
+    table_dev.record_stream(torch.cuda.current_stream(dev))
+    return [(big[l, 0], big[l, 1]) for l in range(L)], keep_idx
+
+
 # ------------------------------------------------------------------------------------------------------
 # RTL-ordered stages (parity unpinned): local V pruning and head pruning
 # ------------------------------------------------------------------------------------------------------
