@@ -245,6 +245,10 @@ typedef struct SpattenPrefillArgs {
   int64_t logits_stride_b, logits_stride_h, logits_stride_q;   /* elements */
   void* probs;              /* scratch fp16, same strides */
   void* out;                /* fp16 [b, q_len, H, D] */
+  float* importance;        /* optional fp32 [b, H, importance_stride]: += sum over the q_len query rows of the softmax
+                               probabilities (column sums of P: the cumulative token importance of README.md:21, SURVEY.md
+                               8f rank 2); one extra pass over `probs` */
+  int64_t importance_stride;/* elements between heads (>= kv_len) */
 } SpattenPrefillArgs;
 int spatten_prefill_attn(const SpattenPrefillArgs* args, void* stream);
 

@@ -82,6 +82,7 @@ class PrefillArgs(C.Structure):
         ("rope", C.c_void_p), ("q_pos", C.c_void_p), ("mask", C.c_void_p),
         ("logits", C.c_void_p), ("logits_stride_b", C.c_int64), ("logits_stride_h", C.c_int64),
         ("logits_stride_q", C.c_int64), ("probs", C.c_void_p), ("out", C.c_void_p),
+        ("importance", C.c_void_p), ("importance_stride", C.c_int64),
     ]
 
 

@@ -113,6 +113,8 @@ struct PrefillParams {
   __half* out;              // [b, q_len, H, D]
   int batch, H, n_rep, q_len, kv_len, rope_len;
   float sqrt_d, rsqrt_d;
+  float* importance;        // optional [b, H, imp_stride]: += column sums of P
+  int64_t imp_stride;
 };
 
 // ---- 1. S = rope(Q) . rope(K)^T -----------------------------------------------------------------------------------
@@ -436,6 +438,44 @@ __global__ void __launch_bounds__(kUThreads) umma_pv_kernel(const PrefillParams 
   if (warp == 0) tmem_dealloc(tmem, D < 32 ? 32 : D);
 }
 
+// importance[b, h, j] += sum_q P[b, h, q, j]: the column sums of the probability matrix (cumulative token importance).
+// A flash-style kernel never materialises P; this path keeps it as the fp16 scratch the P.V tiles read anyway, so the
+// column sums are one more streaming pass over it: a thread owns 8 adjacent columns (one 16-byte load per row), a CTA
+// 1024 columns x kColsumRows rows; one atomicAdd per (thread, column) at the end.
+constexpr int kColsumThreads = 128;
+constexpr int kColsumRows = 1024;
+__global__ void __launch_bounds__(kColsumThreads) prob_colsum_kernel(const PrefillParams p) {
+  const int bh = blockIdx.z, h = bh % p.H, b = bh / p.H;
+  const int j0 = (blockIdx.x * kColsumThreads + threadIdx.x) * 8;
+  if (j0 >= p.kv_len) return;
+  const int r0 = blockIdx.y * kColsumRows, r1 = min(p.q_len, r0 + kColsumRows);
+  const __half* P = p.probs + b * p.ls_b + h * p.ls_h;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  const bool vec = j0 + 8 <= p.kv_len && (p.ls_q % 8) == 0 && (reinterpret_cast<uintptr_t>(P) & 15) == 0;
+  if (vec) {
+#pragma unroll 4
+    for (int r = r0; r < r1; ++r) {
+      const uint4 v = __ldcs(reinterpret_cast<const uint4*>(P + static_cast<int64_t>(r) * p.ls_q + j0));
+      const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h2[e]);
+        acc[2 * e] += f.x;
+        acc[2 * e + 1] += f.y;
+      }
+    }
+  } else {
+    for (int r = r0; r < r1; ++r)
+      for (int e = 0; e < 8 && j0 + e < p.kv_len; ++e) acc[e] += __half2float(P[static_cast<int64_t>(r) * p.ls_q + j0 + e]);
+  }
+  float* imp = p.importance + (static_cast<int64_t>(b) * p.H + h) * p.imp_stride + j0;
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+    if (j0 + e < p.kv_len && acc[e] != 0.f) atomicAdd(imp + e, acc[e]);
+}
+
 }  // namespace spatten
 
 using namespace spatten;
@@ -449,6 +489,8 @@ extern "C" int spatten_prefill_attn(const SpattenPrefillArgs* a, void* stream) {
   SPATTEN_CHECK_ARG(a->q && a->k_cache && a->v_cache && a->rope && a->q_pos && a->logits && a->probs && a->out,
                     "spatten_prefill_attn: NULL pointer");
   SPATTEN_CHECK_ARG(a->logits_stride_q >= a->kv_len, "spatten_prefill_attn: logits_stride_q < kv_len");
+  SPATTEN_CHECK_ARG(a->importance == nullptr || a->importance_stride >= a->kv_len,
+                    "spatten_prefill_attn: importance_stride < kv_len");
   const uintptr_t al = reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k_cache) |
                        reinterpret_cast<uintptr_t>(a->v_cache) | reinterpret_cast<uintptr_t>(a->rope) |
                        reinterpret_cast<uintptr_t>(a->out);
@@ -482,6 +524,12 @@ extern "C" int spatten_prefill_attn(const SpattenPrefillArgs* a, void* stream) {
   const int64_t rows = static_cast<int64_t>(a->batch) * a->num_heads * a->q_len;
   softmax_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(p);
   umma_pv_kernel<D><<<dim3(1, mt, bh), kUThreads, smem_pv, st>>>(p);
+  if (a->importance != nullptr) {
+    p.importance = a->importance;
+    p.imp_stride = a->importance_stride;
+    prob_colsum_kernel<<<dim3((a->kv_len + kColsumThreads * 8 - 1) / (kColsumThreads * 8),
+                              (a->q_len + kColsumRows - 1) / kColsumRows, bh), kColsumThreads, 0, st>>>(p);
+  }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? SPATTEN_OK : cuda_fail(e, "spatten_prefill_attn launch");
 }

@@ -237,12 +237,14 @@ class DecodeStep:
 
 
 def prefill_attn(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, kv_len: int, rope: torch.Tensor,
-                 q_pos: torch.Tensor, mask: Optional[torch.Tensor] = None, logits: Optional[torch.Tensor] = None):
+                 q_pos: torch.Tensor, mask: Optional[torch.Tensor] = None, logits: Optional[torch.Tensor] = None,
+                 importance: Optional[torch.Tensor] = None):
     """Prefill / chunk attention on the tcgen05 tensor cores -- `spatten_prefill_attn` (head_dim 128).
 
     q fp16 [b,q_len,H,D] un-rotated; the new K/V rows are already in k_cache/v_cache [b,H_kv,cap,D]; kv_len rows
     valid; q_pos int64 [b,q_len]; mask fp16 additive [b,q_len,kv_len].  Returns (out [b,q_len,H,D],
-    logits [b,H,q_len,kv_len] == attn_scores).
+    logits [b,H,q_len,kv_len] == attn_scores).  `importance` fp32 [b,H,>=kv_len] accumulates the column sums of the
+    softmax probabilities (cumulative token importance) in place.
     """
     lib = _lib.load()
     _require_cuda(q, k_cache, v_cache, rope, q_pos, mask, logits)
@@ -275,6 +277,12 @@ def prefill_attn(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, 
             raise ValueError("mask must be contiguous fp16 [b, q_len, kv_len]")
         a.mask = mask.data_ptr()
     a.logits, a.probs, a.out = logits.data_ptr(), probs.data_ptr(), out.data_ptr()
+    if importance is not None:
+        if (importance.dtype != torch.float32 or importance.dim() != 3 or importance.shape[:2] != (b, H)
+                or importance.shape[2] < kv_len or importance.stride(2) != 1 or importance.stride(0) != H * importance.stride(1)):
+            raise ValueError("importance must be fp32 [b, H, >= kv_len] with contiguous tokens")
+        _require_cuda(importance)
+        a.importance, a.importance_stride = importance.data_ptr(), importance.stride(1)
     a.logits_stride_b, a.logits_stride_h, a.logits_stride_q = logits.stride(0), logits.stride(1), logits.stride(2)
     with torch.cuda.device(q.device):
         _lib.check(lib.spatten_prefill_attn(C.byref(a), C.c_void_p(_stream_ptr(q.device))))

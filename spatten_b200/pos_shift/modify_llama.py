@@ -39,6 +39,18 @@ def _grow(past: Optional[torch.Tensor], b, H_kv, D, have, need, device) -> Cache
     return CacheBuffer(buf, have)
 
 
+def _token_importance(self, bsz: int, H: int, need: int):
+    """Optional cumulative token importance (README.md:21): a module attribute `spatten_token_importance`, fp32
+    [b, H, capacity], set by the caller; every forward adds its softmax probabilities (decode: one row; prefill: the
+    column sums over the query rows).  None = not tracked (the reference Python path prunes on last-step logits only)."""
+    imp = getattr(self, "spatten_token_importance", None)
+    if imp is None:
+        return None
+    if imp.dtype != torch.float32 or imp.dim() != 3 or imp.shape[0] != bsz or imp.shape[1] != H or imp.shape[2] < need:
+        raise ValueError(f"spatten_token_importance must be fp32 [{bsz}, {H}, >= {need}], got {tuple(imp.shape)} {imp.dtype}")
+    return imp
+
+
 def _rope_for(self, device, need: int) -> torch.Tensor:
     tab = getattr(self, "_spatten_rope", None)
     if tab is None or tab.shape[0] < need or tab.device != device:
@@ -107,7 +119,8 @@ def llama_pos_shift_attention_forward(
                               q_pos=position_ids.reshape(bsz), mask=mask,
                               logits=scores.view(bsz, H, kv_seq_len),
                               head_mask=getattr(self, "spatten_head_mask", None),
-                              head_importance=getattr(self, "spatten_head_importance", None))
+                              head_importance=getattr(self, "spatten_head_importance", None),
+                              importance=_token_importance(self, bsz, H, kv_seq_len))
     else:
         # prefill / chunk: store the new K/V rows (:95-100), then score every query row against the cache
         kbuf[:, :, past_len:kv_seq_len].copy_(k_new.transpose(1, 2))
@@ -116,7 +129,8 @@ def llama_pos_shift_attention_forward(
         head_mask = getattr(self, "spatten_head_mask", None)
         if D == 128 and head_mask is None and q_len >= 16:
             # dense tiles: Q.K^T and P.V on the tcgen05 tensor cores (spatten_prefill_attn)
-            out, _ = ops.prefill_attn(q, kbuf, vbuf, kv_seq_len, rope, position_ids.reshape(bsz, q_len), mask, scores)
+            out, _ = ops.prefill_attn(q, kbuf, vbuf, kv_seq_len, rope, position_ids.reshape(bsz, q_len), mask, scores,
+                                      importance=_token_importance(self, bsz, H, kv_seq_len))
         else:
             # short chunks / other head sizes / pruned heads: one decode-kernel row per (query, head)
             out = ops.decode_attn(q, kbuf, vbuf, kv_seq_len, rope, q_pos=position_ids.reshape(bsz, q_len), mask=mask,

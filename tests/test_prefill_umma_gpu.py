@@ -87,3 +87,29 @@ def test_prefill_umma_full_size_8192_sampled_rows_vs_oracle():
     probs = torch.softmax((ref_scores + mask[:, :, rows]).float(), dim=-1).to(torch.float16)
     ref_out = torch.matmul(probs, v)                                          # [b, H, rows, D]
     assert rel_err(out[:, rows.to(dev)].cpu(), ref_out.transpose(1, 2)) <= OUT_REL_TOL
+
+
+@pytest.mark.parametrize("b,H,past,q_len", [(1, 4, 0, 300), (2, 2, 130, 257), (1, 2, 0, 2048)])
+def test_prefill_importance_column_sums(b, H, past, q_len):
+    """importance[b,h,j] += sum_q softmax(S + mask)[b,h,q,j] == oracle.softmax_importance per sequence (parity-unpinned
+    restatement of README.md:21's cumulative token importance); accumulates across calls."""
+    from spatten_b200 import ops
+    D, kv, dev = 128, past + q_len, "cuda"
+    seed = 8800 + past + q_len
+    q = det_normal((b, H, q_len, D), seed, 1.0, torch.float16)
+    k = det_normal((b, H, kv, D), seed + 1, 1.0, torch.float16)
+    v = det_normal((b, H, kv, D), seed + 2, 1.0, torch.float16)
+    pos = torch.arange(past, kv).unsqueeze(0).expand(b, q_len).contiguous()
+    mask = causal_mask(b, q_len, past, torch.float16)
+    imp = torch.zeros((b, H, kv + 3), dtype=torch.float32, device=dev)
+    args = (q.transpose(1, 2).contiguous().to(dev), k.to(dev), v.to(dev), kv, ops.rope_table(D, kv, dev), pos.to(dev),
+            mask[:, 0].contiguous().to(dev))
+    _, logits = ops.prefill_attn(*args, importance=imp)
+    torch.cuda.synchronize()
+    ref = torch.stack([O.softmax_importance(logits[i:i + 1].cpu(), mask[i:i + 1]) for i in range(b)])     # [b, H, kv]
+    assert torch.allclose(imp[..., :kv].cpu(), ref, rtol=2e-3, atol=2e-4)
+    assert (imp[..., kv:] == 0).all()
+    assert abs(float(imp.sum()) - b * H * q_len) / (b * H * q_len) < 1e-3      # every row of P sums to one
+    ops.prefill_attn(*args, importance=imp)
+    torch.cuda.synchronize()
+    assert torch.allclose(imp[..., :kv].cpu(), 2 * ref, rtol=2e-3, atol=4e-4)
