@@ -354,7 +354,7 @@ def run_ours(args):
         ok = True
         with torch.cuda.stream(stream):
             local_step = ops.DecodeStep(q, kc, vc, kv_len, rope, k_new=kn, v_new=vn, logits=logits, head_mask=head_mask,
-                                        chain=False)
+                                        chain=False, sharded_layout=True)
             mine = local_step.launch(stream.cuda_stream).clone()
             stream.synchronize()
             every = [torch.empty_like(mine) for _ in range(world)]

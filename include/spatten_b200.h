@@ -176,6 +176,9 @@ int spatten_decode_attn_host(const SpattenDecodeArgs* args, const void* q_host, 
  * still written (by the first live head of the kv group, or by the zeroing warp when the whole group is pruned).
  * ---------------------------------------------------------------------------------------------- */
 #define SPATTEN_STEP_CHAIN 1u
+/* Use the work split of the head-sharded build (the one with a communication warp) even without peers, so that a local
+ * launch sums in exactly the order a sharded launch does -- lets a caller check the fused exchange bit for bit. */
+#define SPATTEN_STEP_SHARDED_LAYOUT 2u
 
 typedef struct SpattenStepLayer {   /* one per layer, array in DEVICE memory */
   const void* q;          /* fp16 [b, H, D] un-rotated */

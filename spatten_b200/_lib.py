@@ -19,6 +19,7 @@ DECODE_NO_CLUSTER = 4
 DECODE_SCORES_ONLY = 8
 DECODE_SMALL_TILES = 16
 STEP_CHAIN = 1
+STEP_SHARDED_LAYOUT = 2
 ERR_NAMES = {-1: "SPATTEN_ERR_INVALID", -2: "SPATTEN_ERR_UNSUPPORTED", -3: "SPATTEN_ERR_CUDA",
              -4: "SPATTEN_ERR_WORKSPACE"}
 

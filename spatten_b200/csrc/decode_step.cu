@@ -115,8 +115,8 @@ __device__ __forceinline__ unsigned long long step_gtime() {
   return t;
 }
 
-template <int D, int WARPS, int STAGES, int PASSES, bool DBG = false>
-__global__ void __launch_bounds__(WARPS * 32, 1) decode_step_kernel(const StepParams p) {
+template <int D, int WARPS, int STAGES, int PASSES, bool DBG = false, bool COMM = false>
+__global__ void __launch_bounds__((WARPS + (COMM ? 1 : 0)) * 32, 1) decode_step_kernel(const StepParams p) {
 #define STAMP(layer, k)                                                                                                   \
   do {                                                                                                                   \
     if (DBG && p.dbg && lane == 0)                                                                                       \
@@ -138,6 +138,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) decode_step_kernel(const StepPa
 
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ unsigned cta_ctl[2];                    // [0] layers known complete, [1] layers somebody is polling for
+  // COMM build (head sharding): finished rows are handed to a dedicated communication warp through a small mailbox, so
+  // the NVLink stores and the system-scope release (measured: 3.8 us per layer when a compute warp does them) never
+  // stall a warp that streams K/V.
+  constexpr int kMailSlots = 4;
+  __shared__ __align__(16) __half mail_row[COMM ? kMailSlots : 1][D];
+  __shared__ int mail_meta[COMM ? kMailSlots : 1][2];               // layer, row
+  __shared__ unsigned mail_state[COMM ? kMailSlots : 1];            // 0 free, 1 full
+  __shared__ unsigned mail_ctl[2];                                   // [0] slots claimed, [1] compute warps finished
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 3, c = lane & 7;
   uint8_t* wsm = smem + warp * kWarpSmem;
@@ -157,17 +165,55 @@ __global__ void __launch_bounds__(WARPS * 32, 1) decode_step_kernel(const StepPa
   }
   if (threadIdx.x < step_seg_bufs(WARPS) * 4)
     reinterpret_cast<unsigned*>(segbuf + (threadIdx.x >> 2) * kSegBufFloats + WARPS * D + WARPS * 2)[threadIdx.x & 3] = 0u;
-  if (lane == 0) {
+  if (lane == 0 && warp < WARPS) {
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
     fence_mbar_init();
   }
-  if (threadIdx.x < 2) cta_ctl[threadIdx.x] = 0u;
+  if (threadIdx.x < 2) { cta_ctl[threadIdx.x] = 0u; mail_ctl[threadIdx.x] = 0u; }
+  if (COMM && threadIdx.x < kMailSlots) mail_state[threadIdx.x] = 0u;
   __syncthreads();
 
   const unsigned epoch = *reinterpret_cast<volatile const unsigned*>(p.ctrl);
   const unsigned flag_target = (epoch + 1u) * p.rows;
   const int G = gridDim.x;
+
+  if (COMM && warp == WARPS) {
+    // ---- communication warp: serve the mailbox in claim order until every compute warp has finished ------------------
+    volatile unsigned* mstate = mail_state;
+    volatile unsigned* mctl = mail_ctl;
+    unsigned next = 0;
+    while (true) {
+      const unsigned slot = next % kMailSlots, want = 2u * (next / kMailSlots) + 1u;
+      bool have = false;
+      while (true) {
+        if (mstate[slot] == want) { have = true; break; }
+        if (mctl[1] == static_cast<unsigned>(WARPS) && mctl[0] == next) break;
+        __nanosleep(100);
+      }
+      if (!have) break;
+      __threadfence_block();
+      const int layer = mail_meta[slot][0], row = mail_meta[slot][1];
+      const int64_t off = static_cast<int64_t>(layer) * p.peer_layer_stride + static_cast<int64_t>(row) * D + lane * PER;
+      if (PER == 4) {
+        const uint2 v = *reinterpret_cast<const uint2*>(&mail_row[slot][lane * PER]);
+#pragma unroll 1
+        for (int r = 0; r < p.n_out; ++r) *reinterpret_cast<uint2*>(p.peer_out[r] + off) = v;
+      } else {
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(&mail_row[slot][lane * PER]);
+#pragma unroll 1
+        for (int r = 0; r < p.n_out; ++r) *reinterpret_cast<uint32_t*>(p.peer_out[r] + off) = v;
+      }
+      __syncwarp();
+      if (lane < p.n_flag) {
+        unsigned int* f = p.flag_ptr[lane] + static_cast<int64_t>(layer) * p.flag_layer_stride;
+        asm volatile("fence.acq_rel.sys;\n\tred.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(f) : "memory");
+      }
+      __syncwarp();
+      if (lane == 0) mstate[slot] = want + 1u;          // free for the next generation
+      ++next;
+    }
+  } else {
 
   // ---- work split: layer l's tile list is cut into G contiguous CTA ranges; inside a CTA, warp w takes the tiles at
   //      range positions w, w + WARPS, ... -- so the 8/16 warps of an SM work on neighbouring tiles of (mostly) one row
@@ -293,7 +339,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) decode_step_kernel(const StepPa
 
   // every lane stored its piece of a row of layer `layer`: publish it
   auto signal_row = [&](int layer) {
-    if (p.n_flag == 0) return;
+    if (p.n_flag == 0 || (COMM && p.n_out > 0)) return;      // COMM: the communication warp publishes the row
     __syncwarp();
     if (lane < p.n_flag) {
       unsigned int* f = p.flag_ptr[lane] + static_cast<int64_t>(layer) * p.flag_layer_stride;
@@ -316,6 +362,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) decode_step_kernel(const StepPa
       __half* dst = static_cast<__half*>(lys[layer].out) + off;
       if (PER == 4) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(oh16);
       else *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(oh16);
+    } else if (COMM) {
+      // hand the row to the communication warp: claim a mailbox slot, wait until its previous use has been sent
+      unsigned claim = 0;
+      if (lane == 0) claim = atomicAdd(&mail_ctl[0], 1u);
+      claim = __shfl_sync(0xffffffffu, claim, 0);
+      const unsigned slot = claim % kMailSlots, gen = 2u * (claim / kMailSlots);
+      while (*reinterpret_cast<volatile unsigned*>(&mail_state[slot]) != gen) __nanosleep(40);
+      if (PER == 4) *reinterpret_cast<uint2*>(&mail_row[slot][lane * PER]) = *reinterpret_cast<const uint2*>(oh16);
+      else *reinterpret_cast<uint32_t*>(&mail_row[slot][lane * PER]) = *reinterpret_cast<const uint32_t*>(oh16);
+      if (lane == 0) { mail_meta[slot][0] = layer; mail_meta[slot][1] = row; }
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_block();
+        *reinterpret_cast<volatile unsigned*>(&mail_state[slot]) = gen + 1u;
+      }
     } else {
 #pragma unroll 1
       for (int r = 0; r < p.n_out; ++r) {
@@ -722,6 +783,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) decode_step_kernel(const StepPa
 #pragma unroll 1
     for (int l = p.chain ? p.L - 1 : 0; l < p.L; ++l) wait_layer(l);
   }
+  if (COMM && lane == 0) atomicAdd(&mail_ctl[1], 1u);      // this compute warp will hand over no more rows
+  }   // compute warps
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -747,13 +810,14 @@ constexpr size_t step_smem_bytes() {
 //   2: 12 warps x 2 stages x 16-token tiles   3: 12 warps x 4 stages x 8-token tiles
 //   4: 8 x 2 x 16 tok   5: 8 x 2 x 8 tok   6: 16 x 2 x 8 tok   7: 8 x 4 x 8 tok  (shallower rings: less queueing in front of
 //   the latency-critical query / flag loads)
-constexpr int kStepVariants = 9;
+constexpr int kStepVariants = 10;
 constexpr int kStepMaxWarps = 16;
 using StepKernel = void (*)(const StepParams);
 struct StepVariant {
   StepKernel kernel;
   int warps, tile;
   size_t smem;
+  int comm = 0;            // 1: one extra warp per CTA that does the NVLink stores and system-scope releases
 };
 template <int D>
 static StepVariant step_variant(int v) {
@@ -765,6 +829,7 @@ static StepVariant step_variant(int v) {
   if (v == 6) return {decode_step_kernel<D, 16, 2, 2>, 16, 8, step_smem_bytes<D, 16, 2, 2>()};
   if (v == 7) return {decode_step_kernel<D, 8, 4, 2>, 8, 8, step_smem_bytes<D, 8, 4, 2>()};
   if (v == 8) return {decode_step_kernel<D, 8, 3, 4, true>, 8, 16, step_smem_bytes<D, 8, 3, 4>()};   // timeline build
+  if (v == 9) return {decode_step_kernel<D, 8, 2, 4, false, true>, 8, 16, step_smem_bytes<D, 8, 2, 4>(), 1};   // + communication warp
   return {decode_step_kernel<D, 8, 3, 4>, 8, 16, step_smem_bytes<D, 8, 3, 4>()};
 }
 // Measured on B200 (profiles/r2_step_variants.jsonl): with few tiles per warp and layer (BASELINE config 2: 27.7
@@ -775,11 +840,15 @@ static int step_variant_choice(long tiles_per_layer, int sms) {
   static int forced = -2;
   if (forced == -2) {
     const char* e = getenv("SPATTEN_STEP_VARIANT");
-    forced = (e && e[0] >= '0' && e[0] < '0' + kStepVariants) ? e[0] - '0' : -1;
+    forced = e ? atoi(e) : -1;
+    if (forced < 0 || forced >= kStepVariants) forced = -1;
   }
   if (forced >= 0) return forced;
   return tiles_per_layer >= 64L * sms ? 4 : 2;
 }
+
+// the same choice among the builds that carry a communication warp
+static int step_comm_variant(long, int) { return 9; }   // 8 warps x 2 stages + communication warp (a 12-warp build does not fit)
 
 template <int D>
 static int step_grid(int variant, int& grid) {
@@ -791,7 +860,7 @@ static int step_grid(int variant, int& grid) {
   cudaError_t e = cudaFuncSetAttribute(sv.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sv.smem));
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(decode_step_kernel)");
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sv.kernel, sv.warps * 32, sv.smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sv.kernel, (sv.warps + sv.comm) * 32, sv.smem);
   if (e != cudaSuccess || per_sm < 1) return cuda_fail(e, "decode_step_kernel does not fit on an SM");
   const int sms = sm_count();
   if (sms <= 0) return SPATTEN_ERR_CUDA;
@@ -870,7 +939,8 @@ extern "C" int spatten_decode_step(const SpattenStepArgs* a, void* stream) {
   const long tiles16 = static_cast<long>(a->batch) * a->num_heads * ((n_total + 15) / 16);
   const int sms_now = sm_count();
   if (sms_now <= 0) return SPATTEN_ERR_CUDA;
-  const int variant = g_step_dbg ? 8 : step_variant_choice(tiles16, sms_now);
+  // head sharding over NVLink: the build with a communication warp (unless a variant is forced for measurements)
+  const int variant = g_step_dbg ? 8 : (((a->n_peers > 1 || (a->flags & SPATTEN_STEP_SHARDED_LAYOUT)) && !getenv("SPATTEN_STEP_VARIANT")) ? step_comm_variant(tiles16, sms_now) : step_variant_choice(tiles16, sms_now));
   if (int rc = (a->head_dim == 128 ? step_grid<128>(variant, grid) : step_grid<64>(variant, grid))) return rc;
   const StepVariant sv = a->head_dim == 128 ? step_variant<128>(variant) : step_variant<64>(variant);
 
@@ -942,7 +1012,7 @@ extern "C" int spatten_decode_step(const SpattenStepArgs* a, void* stream) {
 
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(sv.warps * 32);
+  cfg.blockDim = dim3((sv.warps + sv.comm) * 32);
   cfg.dynamicSmemBytes = sv.smem;
   cfg.stream = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaLaunchKernelEx(&cfg, sv.kernel, p);

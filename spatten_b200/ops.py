@@ -157,7 +157,8 @@ class DecodeStep:
     """
 
     def __init__(self, q, k_caches, v_caches, kv_len: int, rope, k_new=None, v_new=None, q_pos=None, out=None,
-                 logits=None, importance=None, head_mask=None, head_importance=None, chain: bool = True):
+                 logits=None, importance=None, head_mask=None, head_importance=None, chain: bool = True,
+                 sharded_layout: bool = False):
         lib = _lib.load()
         _require_cuda(q, rope, k_new, v_new, q_pos, out, logits, importance, head_mask, head_importance, *k_caches, *v_caches)
         L, b, H, D = q.shape
@@ -209,7 +210,7 @@ class DecodeStep:
         a.struct_size = C.sizeof(_lib.StepArgs)
         a.num_layers, a.batch, a.num_heads, a.num_kv_heads, a.head_dim = L, b, H, H_kv, D
         a.kv_len, a.rope_len, a.append = int(kv_len), rope.shape[0], int(append)
-        a.flags = _lib.STEP_CHAIN if chain else 0
+        a.flags = (_lib.STEP_CHAIN if chain else 0) | (_lib.STEP_SHARDED_LAYOUT if sharded_layout else 0)
         a.layers = self.table.data_ptr()
         a.cache_stride_b, a.cache_stride_h = st[0], st[1]
         a.logits_stride = logits.stride(2) if logits is not None else 0

@@ -82,7 +82,7 @@ for chain in (True, False):
     pxs = PeerStepExchange(step, sh)
     # this rank's heads through the same step kernel without the exchange: the bit-exact reference for every slot
     local = ops.DecodeStep(q[:, :, s].contiguous(), [k.clone() for k in kcs2], [v.clone() for v in vcs2], n, rope,
-                           k_new=kn[:, :, s].contiguous(), v_new=vn[:, :, s].contiguous(), chain=chain)
+                           k_new=kn[:, :, s].contiguous(), v_new=vn[:, :, s].contiguous(), chain=chain, sharded_layout=True)
     mine = local.launch().clone()
     torch.cuda.synchronize()
     every = [torch.empty_like(mine) for _ in range(world)]
