@@ -362,6 +362,28 @@ typedef struct SpattenSparsePvArgs {
 } SpattenSparsePvArgs;
 int spatten_sparse_pv(const SpattenSparsePvArgs* args, void* stream);
 
+/* The same RTL-ordered path in ONE launch: DotProduct over all kv_len cached keys -> TopK(keep) -> MultiplyValue over the
+ * survivors, one thread-block cluster per (sequence, head) row, logits and the survivor list kept in (distributed)
+ * shared memory between the stages.  The query's own K/V row must already be in the cache (append it first);
+ * kv_len <= 65408.  Outputs: out fp16 [batch, num_heads, head_dim]; logits fp16 [batch*num_heads, logits_stride] (all
+ * kv_len scores); keep_idx int32 [batch*num_heads, keep_stride] ascending (min(keep, kv_len) entries). */
+typedef struct SpattenLocalVArgs {
+  uint32_t struct_size;
+  int32_t batch, num_heads, num_kv_heads, head_dim, kv_len, rope_len, keep;
+  const void* q;                             /* fp16 [batch, num_heads, head_dim] un-rotated */
+  const void* k_cache;                       /* fp16 [batch, num_kv_heads, >= kv_len, head_dim] un-rotated */
+  const void* v_cache;
+  int64_t cache_stride_b, cache_stride_h;    /* elements */
+  const void* rope;                          /* fp16 [rope_len, head_dim] */
+  const int64_t* q_pos;                      /* [batch] or NULL = kv_len - 1 */
+  void* out;
+  void* logits;
+  int64_t logits_stride;
+  int32_t* keep_idx;
+  int64_t keep_stride;
+} SpattenLocalVArgs;
+int spatten_local_v_attn(const SpattenLocalVArgs* args, void* stream);
+
 /* Progressive quantisation of the KV cache (README.md:11 "KV progressive quantization"; BASELINE config 4).
  * Per (batch, kv head): K and V each stored as an MSB and an LSB 4-bit plane, u8 [tokens, head_dim/2], of the
  * offset-128 int8 code u = clamp(rint(x / scale), -127, 127) + 128 (msb = u >> 4, lsb = u & 15), plus one fp16

@@ -133,6 +133,18 @@ class SparsePvArgs(C.Structure):
     ]
 
 
+class LocalVArgs(C.Structure):
+    """Mirror of `SpattenLocalVArgs`."""
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("batch", C.c_int32), ("num_heads", C.c_int32), ("num_kv_heads", C.c_int32),
+        ("head_dim", C.c_int32), ("kv_len", C.c_int32), ("rope_len", C.c_int32), ("keep", C.c_int32),
+        ("q", C.c_void_p), ("k_cache", C.c_void_p), ("v_cache", C.c_void_p),
+        ("cache_stride_b", C.c_int64), ("cache_stride_h", C.c_int64),
+        ("rope", C.c_void_p), ("q_pos", C.c_void_p), ("out", C.c_void_p), ("logits", C.c_void_p),
+        ("logits_stride", C.c_int64), ("keep_idx", C.c_void_p), ("keep_stride", C.c_int64),
+    ]
+
+
 class QuantKV(C.Structure):
     """Mirror of `SpattenQuantKV`."""
     _fields_ = [
@@ -195,6 +207,7 @@ def _bind_optional(lib):
     lib.spatten_kv_gather.argtypes = [C.POINTER(GatherArgs), C.c_void_p]
     lib.spatten_prune_layers.argtypes = [C.POINTER(PruneLayersArgs), C.c_void_p]
     lib.spatten_sparse_pv.argtypes = [C.POINTER(SparsePvArgs), C.c_void_p]
+    lib.spatten_local_v_attn.argtypes = [C.POINTER(LocalVArgs), C.c_void_p]
     lib.spatten_prefill_attn.argtypes = [C.POINTER(PrefillArgs), C.c_void_p]
     lib.spatten_wait_flags.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.spatten_kv_quantize.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32,

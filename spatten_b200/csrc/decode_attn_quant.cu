@@ -63,17 +63,18 @@ __device__ __forceinline__ float q_div_by_const(float x, float c, float rc) {
 // (16*m + l) - 128, or the MSB bucket midpoint (16*m + 8) - 128 when the LSB plane is not fetched.
 template <bool LSB>
 __device__ __forceinline__ void deq8(uint32_t wm, uint32_t wl, __half2 (&x)[4]) {
-  const __half2 k1024 = __half2half2(__ushort_as_half(0x6400));                 // 1024
+  // A nibble OR-ed into mantissa bits 4..7 of the fp16 pattern 0x6400 (= 1024) reads as 1024 + 16*m, so the MSB code
+  // 16*m needs no multiply: one shift (none for i = 1), one LOP3, one HADD2 per pair of dims, all exact.
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const uint32_t bm = ((wm >> (4 * i)) & 0x000f000fu) | 0x64006400u;           // (1024 + m_2i, 1024 + m_2i+1)
-    const __half2 m = __hsub2(*reinterpret_cast<const __half2*>(&bm), k1024);   // exact
+    const uint32_t sh = i == 0 ? (wm << 4) : (i == 1 ? wm : (wm >> (4 * i - 4)));
+    const uint32_t bm = (sh & 0x00f000f0u) | 0x64006400u;                        // (1024 + 16 m_2i, 1024 + 16 m_2i+1)
     if (LSB) {
-      const uint32_t bl = ((wl >> (4 * i)) & 0x000f000fu) | 0x64006400u;
-      const __half2 lo = __hsub2(*reinterpret_cast<const __half2*>(&bl), __float2half2_rn(1152.f));   // l - 128
-      x[i] = __hfma2(m, __float2half2_rn(16.f), lo);                              // exact: |value| <= 128
+      const uint32_t bl = ((wl >> (4 * i)) & 0x000f000fu) | 0x64006400u;         // (1024 + l_2i, 1024 + l_2i+1)
+      const __half2 hi = __hadd2(*reinterpret_cast<const __half2*>(&bm), __float2half2_rn(-1152.f));   // 16 m - 128
+      x[i] = __hadd2(hi, __hadd2(*reinterpret_cast<const __half2*>(&bl), __float2half2_rn(-1024.f)));   // + l, exact
     } else {
-      x[i] = __hfma2(m, __float2half2_rn(16.f), __float2half2_rn(-120.f));
+      x[i] = __hadd2(*reinterpret_cast<const __half2*>(&bm), __float2half2_rn(-1144.f));             // 16 m + 8 - 128
     }
   }
 }
@@ -134,8 +135,8 @@ __global__ void __launch_bounds__(kQThreads, 1) decode_attn_q4_kernel(const Quan
   }
   __syncwarp();
 
-  // query: fp16 RoPE at its position, kept as fp32 (same as the fp16 kernel); lane holds dims c*8.. and 64+c*8..
-  float ql[8], qh[8];
+  // query: fp16 RoPE at its position, kept as the fp16 values themselves (FHFMA operands); lane holds dims c*8.. and 64+c*8..
+  __half2 qlr[4], qhr[4];
   {
     int64_t pos = p.q_pos ? p.q_pos[bi] : p.kv_len - 1;
     pos = max(static_cast<int64_t>(0), min(pos, static_cast<int64_t>(p.rope_len - 1)));
@@ -147,9 +148,8 @@ __global__ void __launch_bounds__(kQThreads, 1) decode_attn_q4_kernel(const Quan
     const __half2* c2 = reinterpret_cast<const __half2*>(&cs); const __half2* s2 = reinterpret_cast<const __half2*>(&sn);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float2 fl = __half22float2(__hsub2_rn(__hmul2_rn(a2[i], c2[i]), __hmul2_rn(b2[i], s2[i])));
-      const float2 fh = __half22float2(__hadd2_rn(__hmul2_rn(b2[i], c2[i]), __hmul2_rn(a2[i], s2[i])));
-      ql[2 * i] = fl.x; ql[2 * i + 1] = fl.y; qh[2 * i] = fh.x; qh[2 * i + 1] = fh.y;
+      qlr[i] = __hsub2_rn(__hmul2_rn(a2[i], c2[i]), __hmul2_rn(b2[i], s2[i]));
+      qhr[i] = __hadd2_rn(__hmul2_rn(b2[i], c2[i]), __hmul2_rn(a2[i], s2[i]));
     }
   }
   float m = -CUDART_INF_F, l = 0.f, accl[8], acch[8];
@@ -194,10 +194,10 @@ __global__ void __launch_bounds__(kQThreads, 1) decode_attn_q4_kernel(const Quan
         float d0 = 0.f, d1 = 0.f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float2 fl = __half22float2(__hsub2_rn(__hmul2_rn(kl[e], c2[e]), __hmul2_rn(kh[e], s2[e])));
-          const float2 fh = __half22float2(__hadd2_rn(__hmul2_rn(kh[e], c2[e]), __hmul2_rn(kl[e], s2[e])));
-          d0 = fmaf(ql[2 * e], fl.x, d0); d0 = fmaf(ql[2 * e + 1], fl.y, d0);
-          d1 = fmaf(qh[2 * e], fh.x, d1); d1 = fmaf(qh[2 * e + 1], fh.y, d1);
+          const __half2 rl = __hsub2_rn(__hmul2_rn(kl[e], c2[e]), __hmul2_rn(kh[e], s2[e]));
+          const __half2 rh = __hadd2_rn(__hmul2_rn(kh[e], c2[e]), __hmul2_rn(kl[e], s2[e]));
+          d0 = fhfma_lo(rl, qlr[e], d0); d0 = fhfma_hi(rl, qlr[e], d0);      // exact fp16 x fp16 products, fp32 sums
+          d1 = fhfma_lo(rh, qhr[e], d1); d1 = fhfma_hi(rh, qhr[e], d1);
         }
         d[ps] = d0 + d1;
       }
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(kQThreads, 1) decode_attn_q4_kernel(const Quan
           const bool valid = tl < ntok;
           const float pr = valid ? fast_exp2((sc[ps] - m) * kLog2eQ) : 0.f;
           l += pr;
-          const float pw = pr * vs[ps];
+          const __half2 pw = __float2half2_rn(pr * vs[ps]);      // probability x value scale, fp16 operand of the FHFMAs
           // invalid rows of a partial stage hold stale bytes: every nibble pattern still dequantises to a finite
           // integer, and pw is exactly 0 for them
           const uint32_t wml = *reinterpret_cast<const uint32_t*>(st + 2 * kPlaneTile + tl * kPlaneRow + c * 4);
@@ -252,9 +252,8 @@ __global__ void __launch_bounds__(kQThreads, 1) decode_attn_q4_kernel(const Quan
           }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float2 fl = __half22float2(vl[e]), fh = __half22float2(vh[e]);
-            accl[2 * e] = fmaf(pw, fl.x, accl[2 * e]); accl[2 * e + 1] = fmaf(pw, fl.y, accl[2 * e + 1]);
-            acch[2 * e] = fmaf(pw, fh.x, acch[2 * e]); acch[2 * e + 1] = fmaf(pw, fh.y, acch[2 * e + 1]);
+            accl[2 * e] = fhfma_lo(vl[e], pw, accl[2 * e]); accl[2 * e + 1] = fhfma_hi(vl[e], pw, accl[2 * e + 1]);
+            acch[2 * e] = fhfma_lo(vh[e], pw, acch[2 * e]); acch[2 * e + 1] = fhfma_hi(vh[e], pw, acch[2 * e + 1]);
           }
         }
       }
@@ -280,50 +279,58 @@ __global__ void __launch_bounds__(kQThreads, 1) decode_attn_q4_kernel(const Quan
   }
 }
 
-// ---- merge kernel: one warp per row; pass 1 also takes the requant decision ----------------------------------
+// ---- merge kernel: one CTA of D threads per row (thread = output dim); pass 1 also takes the requant decision -------
+// The split weights are computed once per row by the first warps and shared through shared memory; every thread then
+// walks the row's partials with 16 independent coalesced loads in flight (the old one-warp-per-row loop was a chain of
+// ~10 dependent L2 round trips: 21 us for 32 rows).
+constexpr int kQMergeMaxSplits = 512;
 template <bool LSB>
-__global__ void quant_merge_kernel(const QuantDecodeParams p) {
+__global__ void __launch_bounds__(128) quant_merge_kernel(const QuantDecodeParams p) {
   constexpr int D = 128;
-  const int row = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= p.rows) return;
+  __shared__ float s_w[kQMergeMaxSplits];
+  __shared__ float s_red[8];
+  const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (LSB && p.need[row] == 0) return;                  // pass 2 touches replayed rows only
   const float* rec = p.part + static_cast<int64_t>(row) * p.n_splits * D;
   const float2* ml = p.part_ml + static_cast<int64_t>(row) * p.n_splits;
+  float2 mine[kQMergeMaxSplits / 128];
   float M = -CUDART_INF_F;
-  for (int s = lane; s < p.n_splits; s += 32) M = fmaxf(M, ml[s].x);
+#pragma unroll
+  for (int k = 0; k < kQMergeMaxSplits / 128; ++k) {
+    const int s = tid + k * 128;
+    mine[k] = s < p.n_splits ? __ldcg(ml + s) : make_float2(-CUDART_INF_F, 0.f);
+    M = fmaxf(M, mine[k].x);
+  }
   M = warp_max(M);
-  float L = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int s = lane; s < p.n_splits; s += 32) {
-    const float2 v = ml[s];
-    L = fmaf(v.y, (M > -CUDART_INF_F) ? fast_exp2((v.x - M) * kLog2eQ) : 0.f, L);
+  if (lane == 0) s_red[warp] = M;
+  __syncthreads();
+  M = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+  float L = 0.f;
+#pragma unroll
+  for (int k = 0; k < kQMergeMaxSplits / 128; ++k) {
+    const int s = tid + k * 128;
+    const float w = (M > -CUDART_INF_F) ? fast_exp2((mine[k].x - M) * kLog2eQ) : 0.f;
+    if (s < p.n_splits) s_w[s] = w;
+    L = fmaf(mine[k].y, w, L);
   }
   L = warp_sum(L);
-  // partial outputs: 8 independent 16-byte loads in flight per lane (the loop is latency bound otherwise)
+  if (lane == 0) s_red[4 + warp] = L;
+  __syncthreads();
+  L = s_red[4] + s_red[5] + s_red[6] + s_red[7];
+  float o = 0.f;
+  constexpr int kU = 16;
 #pragma unroll 1
-  for (int s0 = 0; s0 < p.n_splits; s0 += 8) {
-    float4 a[8];
-    float w[8];
+  for (int s0 = 0; s0 < p.n_splits; s0 += kU) {
+    float v[kU];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int s = min(s0 + u, p.n_splits - 1);
-      a[u] = *reinterpret_cast<const float4*>(rec + static_cast<int64_t>(s) * D + lane * 4);
-      const float mv = ml[s].x;
-      w[u] = (s0 + u < p.n_splits && M > -CUDART_INF_F) ? fast_exp2((mv - M) * kLog2eQ) : 0.f;
-    }
+    for (int u = 0; u < kU; ++u) v[u] = __ldcg(rec + static_cast<int64_t>(min(s0 + u, p.n_splits - 1)) * D + tid);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      o[0] = fmaf(a[u].x, w[u], o[0]); o[1] = fmaf(a[u].y, w[u], o[1]);
-      o[2] = fmaf(a[u].z, w[u], o[2]); o[3] = fmaf(a[u].w, w[u], o[3]);
-    }
+    for (int u = 0; u < kU; ++u) o = fmaf(v[u], (s0 + u < p.n_splits) ? s_w[s0 + u] : 0.f, o);
   }
   const float inv = L > 0.f ? 1.f / L : 0.f;
-  __half2 r0 = __floats2half2_rn(o[0] * inv, o[1] * inv), r1 = __floats2half2_rn(o[2] * inv, o[3] * inv);
-  uint2 pk;
-  pk.x = *reinterpret_cast<uint32_t*>(&r0);
-  pk.y = *reinterpret_cast<uint32_t*>(&r1);
-  *reinterpret_cast<uint2*>(p.out + static_cast<int64_t>(row) * D + lane * 4) = pk;
+  p.out[static_cast<int64_t>(row) * D + tid] = __float2half_rn(o * inv);
   // RequantDecision (RequantDecision.scala:72): the row's largest probability is exp(M - M) / L = 1 / L
-  if (!LSB && lane == 0) p.need[row] = (inv < p.threshold) ? 1 : 0;
+  if (!LSB && tid == 0) p.need[row] = (inv < p.threshold) ? 1 : 0;
 }
 
 // ---- fp16 rows -> planes ---------------------------------------------------------------------------------------
@@ -473,7 +480,7 @@ extern "C" int spatten_decode_attn_quant(const SpattenQuantDecodeArgs* a, void* 
     configured[dev] = true;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int grid = p.n_rg * best, mgrid = (p.rows + 3) / 4;
+  const int grid = p.n_rg * best, mgrid = p.rows;        // merge: one CTA of D threads per row
   decode_attn_q4_kernel<false><<<grid, kQThreads, smem, st>>>(p);           // pass 1: MSB planes
   quant_merge_kernel<false><<<mgrid, 128, 0, st>>>(p);                       //   + RequantDecision
   if (a->requant_threshold > 0.f) {

@@ -476,14 +476,50 @@ def sparse_pv(logits: torch.Tensor, keep_idx: torch.Tensor, v_cache: torch.Tenso
 
 def local_v_attn(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, kv_len: int, rope: torch.Tensor,
                  keep_v: int, k_new: Optional[torch.Tensor] = None, v_new: Optional[torch.Tensor] = None,
-                 q_pos: Optional[torch.Tensor] = None):
+                 q_pos: Optional[torch.Tensor] = None, fused: Optional[bool] = None):
     """RTL stage order (SpAttenController.scala:347-749): DotProduct over ALL cached keys -> TopK(keep_v) ->
-    MultiplyValue over the survivors only.  Three launches, no host sync.  Returns (out [b,H,D], logits
-    [b,H,n], keep_idx int32 [b*H, keep_v] ascending).  HBM traffic: N keys + keep_v values per head.
+    MultiplyValue over the survivors only.  Returns (out [b,H,D], logits [b,H,n], keep_idx int32 [b*H, keep_v]
+    ascending).  HBM traffic: N keys + keep_v values per head.
+
+    One launch (`spatten_local_v_attn`, a thread-block cluster per row) when the new token is already in the cache
+    (k_new is None) and a row slice fits on chip; otherwise -- or with fused=False -- the three-launch path
+    (scores-only decode kernel -> `spatten_topk_select` -> `spatten_sparse_pv`).
     """
     b, H, D = q.shape
     n = int(kv_len) + (1 if k_new is not None else 0)
     logits = torch.empty((b, H, n), dtype=torch.float16, device=q.device)
+    if fused is None:
+        fused = k_new is None and n <= 60000 and keep_v >= 1
+    if fused:
+        if k_new is not None:
+            raise ValueError("local_v_attn(fused=True): append the new K/V row to the cache first")
+        lib = _lib.load()
+        _require_cuda(q, k_cache, v_cache, rope, q_pos)
+        if q.dtype != torch.float16 or k_cache.dtype != torch.float16 or v_cache.dtype != torch.float16:
+            raise TypeError("spatten_b200.local_v_attn: fp16 tensors required")
+        if k_cache.stride(3) != 1 or k_cache.stride(2) != D or v_cache.stride() != k_cache.stride():
+            raise ValueError("spatten_b200.local_v_attn: cache rows must be contiguous with equal K/V strides")
+        q = q.contiguous()
+        keep_n = min(int(keep_v), n)
+        keep = torch.empty((b * H, keep_n), dtype=torch.int32, device=q.device)
+        out = torch.empty((b, H, D), dtype=torch.float16, device=q.device)
+        a = _lib.LocalVArgs()
+        a.struct_size = C.sizeof(_lib.LocalVArgs)
+        a.batch, a.num_heads, a.num_kv_heads, a.head_dim = b, H, k_cache.shape[1], D
+        a.kv_len, a.rope_len, a.keep = n, rope.shape[0], keep_n
+        a.q, a.k_cache, a.v_cache = q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr()
+        a.cache_stride_b, a.cache_stride_h = k_cache.stride(0), k_cache.stride(1)
+        a.rope = rope.data_ptr()
+        if q_pos is not None:
+            if q_pos.dtype != torch.int64 or q_pos.numel() != b:
+                raise TypeError("q_pos must be int64 [b]")
+            q_pos = q_pos.contiguous()
+            a.q_pos = q_pos.data_ptr()
+        a.out, a.logits, a.logits_stride = out.data_ptr(), logits.data_ptr(), logits.stride(1)
+        a.keep_idx, a.keep_stride = keep.data_ptr(), keep.stride(0)
+        with torch.cuda.device(q.device):
+            _lib.check(lib.spatten_local_v_attn(C.byref(a), C.c_void_p(_stream_ptr(q.device))))
+        return out, logits, keep
     a, _, _keep = make_decode_args(q, k_cache, v_cache, kv_len, rope, k_new=k_new, v_new=v_new, q_pos=q_pos,
                                    logits=logits, flags=_lib.DECODE_SCORES_ONLY)
     with torch.cuda.device(q.device):

@@ -36,7 +36,7 @@ def test_struct_layouts_match_c():
       printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(SpattenDecodeArgs), sizeof(SpattenSelectArgs), sizeof(SpattenGatherArgs),
              sizeof(SpattenStepLayer), sizeof(SpattenStepArgs), sizeof(SpattenPrefillArgs), sizeof(SpattenSparsePvArgs),
              sizeof(SpattenQuantDecodeArgs));
-      printf("%zu %zu\n", sizeof(SpattenPruneLayersArgs), sizeof(SpattenPruneLayer));
+      printf("%zu %zu %zu\n", sizeof(SpattenPruneLayersArgs), sizeof(SpattenPruneLayer), sizeof(SpattenLocalVArgs));
       return 0;
     }'''
     with tempfile.TemporaryDirectory() as td:
@@ -46,7 +46,7 @@ def test_struct_layouts_match_c():
         sizes = list(map(int, subprocess.check_output([exe]).split()))
     assert sizes == [C.sizeof(_lib.DecodeArgs), C.sizeof(_lib.SelectArgs), C.sizeof(_lib.GatherArgs),
                      C.sizeof(_lib.StepLayer), C.sizeof(_lib.StepArgs), C.sizeof(_lib.PrefillArgs),
-                     C.sizeof(_lib.SparsePvArgs), C.sizeof(_lib.QuantDecodeArgs), C.sizeof(_lib.PruneLayersArgs), 40]
+                     C.sizeof(_lib.SparsePvArgs), C.sizeof(_lib.QuantDecodeArgs), C.sizeof(_lib.PruneLayersArgs), 40, C.sizeof(_lib.LocalVArgs)]
     assert C.sizeof(_lib.StepLayer) == 64
 
 
