@@ -29,9 +29,9 @@
 
 namespace spatten {
 
-constexpr int kLvWarps = 8;
+constexpr int kLvWarps = 16;         // 4 per scheduler: the DotProduct stage is latency bound with fewer
 constexpr int kLvThreads = kLvWarps * 32;
-constexpr int kLvStages = 3;
+constexpr int kLvStages = 2;
 constexpr int kLvTile = 16;          // tokens per stage: 4 passes of 4 keys x 8 lanes
 constexpr int kLvPasses = 4;
 constexpr int kLvMaxTok = 8192;      // tokens of one row a CTA can hold (logits + survivor list in shared memory)
@@ -222,30 +222,43 @@ __global__ void __launch_bounds__(kLvThreads, 1) local_v_kernel(const LocalVPara
     unsigned kk = p.keep;
 #pragma unroll 1
     for (int shift = 8; shift >= 0; shift -= 8) {
-      sh->hist[tid] = 0;                                       // kLvThreads == 256 bins
+      if (tid < 256) sh->hist[tid] = 0;
       __syncthreads();
-      for (int i = tid; i < ntok_cta; i += kLvThreads) {
-        const uint32_t key = lv_key(s_logit[i]);
-        if (shift == 8 || (key >> 8) == prefix) atomicAdd(&sh->hist[(key >> shift) & 255u], 1u);
+      for (int i0 = 0; i0 < ntok_cta; i0 += kLvThreads) {      // warp-uniform trip count: match_any needs the whole warp
+        const int i = i0 + tid;
+        bool in = i < ntok_cta;
+        uint32_t key = 0;
+        if (in) {
+          key = lv_key(s_logit[i]);
+          in = shift == 8 || (key >> 8) == prefix;
+        }
+        const uint32_t digit = (key >> shift) & 255u;
+        // attention logits crowd into a few exponent buckets: one atomic per distinct digit per warp
+        const unsigned peers = __match_any_sync(0xffffffffu, in ? digit : (256u + lane));
+        if (in && (__ffs(peers) - 1) == lane) atomicAdd(&sh->hist[digit], static_cast<unsigned>(__popc(peers)));
       }
       __syncthreads();
       lv_cluster_sync();
-      // thread t owns bucket 255 - t: total over the cluster, then a descending cumulative count
-      unsigned cnt = 0;
-      for (int cta = 0; cta < C; ++cta) cnt += lv_ld_dsmem_u32(&sh->hist[255 - tid], cta);
-      unsigned incl = cnt;
+      // thread t < 256 owns bucket 255 - t: total over the cluster, then a descending cumulative count
+      unsigned cnt = 0, incl = 0;
+      if (tid < 256) {
+        for (int cta = 0; cta < C; ++cta) cnt += lv_ld_dsmem_u32(&sh->hist[255 - tid], cta);
+        incl = cnt;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
       }
-      if (lane == 31) s_wsum[warp] = incl;
       __syncthreads();
-      unsigned base = 0;
-      for (int w = 0; w < warp; ++w) base += s_wsum[w];
-      incl += base;
-      const unsigned excl = incl - cnt;
-      if (excl < kk && kk <= incl) { s_digit = 255 - tid; s_kk = kk - excl; }
+      if (tid < 256) {
+        unsigned base = 0;
+        for (int w = 0; w < warp; ++w) base += s_wsum[w];
+        incl += base;
+        const unsigned excl = incl - cnt;
+        if (excl < kk && kk <= incl) { s_digit = 255 - tid; s_kk = kk - excl; }
+      }
       __syncthreads();
       prefix = (prefix << 8) | s_digit;
       kk = s_kk;
@@ -324,7 +337,7 @@ __global__ void __launch_bounds__(kLvThreads, 1) local_v_kernel(const LocalVPara
   const int gr = lane / LPR, cl = lane % LPR;                  // V row of the warp-wide load, 4-dim chunk inside the row
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   float lsum = 0.f;
-  constexpr int kU = 16;                                       // V rows in flight per (warp, row group)
+  constexpr int kU = 16;                                       // V rows in flight per (warp, row group): 4 KiB per warp, 64 KiB per SM
 #pragma unroll 1
   for (int e0 = warp * RPW + gr; e0 < nk; e0 += kLvWarps * RPW * kU) {
     uint2 v[kU];

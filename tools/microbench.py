@@ -183,11 +183,11 @@ def bench_extra(iters):
                       "frac_6445": round(kb / us / 1e3 / 6445, 4)}), flush=True)
 
 
-def bench_prefill(iters):
+def bench_prefill(iters, sizes=(1024, 4096, 8192)):
     """Prefill attention core (tcgen05 path) for one Llama-2-7B layer: S x S causal, logits exported."""
     dev, b, H, D = "cuda", 1, 32, 128
     g = torch.Generator(device=dev).manual_seed(5)
-    for S in (1024, 4096, 8192):
+    for S in sizes:
         q = torch.randn((b, S, H, D), generator=g, device=dev, dtype=torch.float16)
         kc = torch.randn((b, H, S, D), generator=g, device=dev, dtype=torch.float16)
         vc = torch.randn((b, H, S, D), generator=g, device=dev, dtype=torch.float16)
@@ -261,6 +261,7 @@ if __name__ == "__main__":
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--extra", action="store_true", help="config-4 quantised decode and Mode-B local-V timings")
     ap.add_argument("--prefill", action="store_true", help="tcgen05 prefill attention timings")
+    ap.add_argument("--prefill-s", type=int, default=None, help="only this prefill length")
     ap.add_argument("--step", action="store_true", help="persistent decode-step kernel timings")
     ap.add_argument("--no-chain", action="store_true")
     ap.add_argument("--step-timeline", action="store_true")
@@ -282,7 +283,7 @@ if __name__ == "__main__":
         bench_extra(a.iters)
         sys.exit(0)
     if a.prefill:
-        bench_prefill(a.iters)
+        bench_prefill(a.iters, (a.prefill_s,) if a.prefill_s else (1024, 4096, 8192))
         sys.exit(0)
     if a.timeline:
         timeline(*map(int, (a.shape or "1,32,128,2048,32").split(",")), flags=a.flags)
