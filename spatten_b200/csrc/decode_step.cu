@@ -36,7 +36,7 @@ namespace spatten {
 constexpr int kStepMaxPeers = 8;
 constexpr int kStepRot = 1;          // work-range rotation per layer (warps)
 constexpr int kStepCtrlWords = 64;   // workspace header: [0] steps completed, [1] exit ticket, [2] wait timed out
-constexpr int kStepSmemLayers = 96;  // layer descriptors staged in shared memory when the model has at most this many
+constexpr int kStepSmemLayers = 80;  // layer descriptors staged in shared memory when the model has at most this many
 
 struct StepParams {
   const SpattenStepLayer* layers;
@@ -70,7 +70,7 @@ struct StepParams {
 };
 
 // CTA-level partial buffers in shared memory = segments a fast warp may run ahead of the slowest warp of its CTA
-__host__ __device__ constexpr int step_seg_bufs(int warps) { return warps <= 8 ? 6 : (warps <= 12 ? 4 : 3); }
+__host__ __device__ constexpr int step_seg_bufs(int warps) { return warps <= 8 ? 6 : 3; }
 
 // One layer's share of work for a CTA: a contiguous range of the layer's (live row, tile) list.
 struct LayerRange {
@@ -115,12 +115,26 @@ __device__ __forceinline__ unsigned long long step_gtime() {
   return t;
 }
 
-template <int D, int WARPS, int STAGES, int PASSES, bool DBG = false, bool COMM = false>
-__global__ void __launch_bounds__((WARPS + (COMM ? 1 : 0)) * 32, 1) decode_step_kernel(const StepParams p) {
+// Shared-memory record of one layer's share of work for this CTA (filled once at kernel start).
+struct RangeRec {
+  int cs, ce;              // tile range [cs, ce) of this CTA in the layer's (live row, tile) list
+  int nlh, vcta;           // live heads of the layer, virtual CTA id (rotates with the layer)
+  unsigned T, geff;        // tiles in the layer, CTAs that take part
+  unsigned long long hm;   // live head bits (valid when head_mask != nullptr)
+};
+
+// Warp roles of a CTA:  WARPS compute warps stream K/V tiles and do nothing else;  one QUERY warp rotates the query of every
+// upcoming segment into shared memory (and is the only one that polls the chain / exchange flags);  one MERGE warp
+// combines the compute warps' partials of a finished segment on chip, publishes the CTA partial, takes the row ticket,
+// merges the row if it was the last CTA, stores the row (locally or into every peer's gather buffer) and releases the
+// flags.  Every global round trip of the merge path (measured: 4.8 us per layer when a streaming warp did it, 3.8 us more
+// for a system-scope release) is off the warps that keep HBM busy.
+template <int D, int WARPS, int STAGES, int PASSES, bool DBG = false>
+__global__ void __launch_bounds__((WARPS + 2) * 32, 1) decode_step_kernel(const StepParams p) {
 #define STAMP(layer, k)                                                                                                   \
   do {                                                                                                                   \
     if (DBG && p.dbg && lane == 0)                                                                                       \
-      p.dbg[((static_cast<size_t>(layer) * gridDim.x + blockIdx.x) * WARPS + warp) * 8 + (k)] = step_gtime();            \
+      p.dbg[((static_cast<size_t>(layer) * gridDim.x + blockIdx.x) * (WARPS + 2) + warp) * 8 + (k)] = step_gtime();      \
   } while (0)
   constexpr int kTile = 4 * PASSES;   // tokens per stage: PASSES passes of 4 keys x 8 lanes
   constexpr int E2 = D / 16;   // halves per lane in each half of the row (8 lanes cover D/2)
@@ -134,18 +148,12 @@ __global__ void __launch_bounds__((WARPS + (COMM ? 1 : 0)) * 32, 1) decode_step_
   constexpr int kTileBytes = kTile * kRowBytes;
   constexpr int kStageBytes = 2 * kTileBytes;
   constexpr int kWarpSmem = STAGES * kStageBytes;
-  constexpr int kSegBufFloats = WARPS * D + WARPS * 2 + 4;      // partials, (m, l) pairs, {count, uses done, pad, pad}
+  constexpr int NB = step_seg_bufs(WARPS);                      // segments in flight per CTA
+  constexpr int kSegBufFloats = WARPS * D + WARPS * 2 + D / 2;  // partials, (m, l) pairs, rotated query (fp16 [D])
 
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ unsigned cta_ctl[2];                    // [0] layers known complete, [1] layers somebody is polling for
-  // COMM build (head sharding): finished rows are handed to a dedicated communication warp through a small mailbox, so
-  // the NVLink stores and the system-scope release (measured: 3.8 us per layer when a compute warp does them) never
-  // stall a warp that streams K/V.
-  constexpr int kMailSlots = 4;
-  __shared__ __align__(16) __half mail_row[COMM ? kMailSlots : 1][D];
-  __shared__ int mail_meta[COMM ? kMailSlots : 1][2];               // layer, row
-  __shared__ unsigned mail_state[COMM ? kMailSlots : 1];            // 0 free, 1 full
-  __shared__ unsigned mail_ctl[2];                                   // [0] slots claimed, [1] compute warps finished
+  // control words per segment buffer: [0] compute warps arrived, [1] uses combined, [2] queries published
+  __shared__ unsigned seg_ctl[NB][4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 3, c = lane & 7;
   uint8_t* wsm = smem + warp * kWarpSmem;
@@ -153,75 +161,21 @@ __global__ void __launch_bounds__((WARPS + (COMM ? 1 : 0)) * 32, 1) decode_step_
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WARPS * kWarpSmem) + warp * STAGES;
   const uint32_t bars_u32 = smem_u32(bars);
   float* segbuf = reinterpret_cast<float*>(smem + WARPS * kWarpSmem + WARPS * STAGES * 8);
-  SpattenStepLayer* lys_s = reinterpret_cast<SpattenStepLayer*>(segbuf + step_seg_bufs(WARPS) * kSegBufFloats);
+  SpattenStepLayer* lys_s = reinterpret_cast<SpattenStepLayer*>(segbuf + NB * kSegBufFloats);
+  RangeRec* ranges = reinterpret_cast<RangeRec*>(lys_s + kStepSmemLayers);
+  const int G = gridDim.x;
 
-  // layer descriptors (64 bytes each, read at every segment start) and the segment buffers' control words
+  // ---- one-time setup: layer descriptors, this CTA's range in every layer, barriers ------------------------------------
   const SpattenStepLayer* lys = p.layers;
   if (p.L <= kStepSmemLayers) {
     uint4* dst = reinterpret_cast<uint4*>(lys_s);
     const uint4* src = reinterpret_cast<const uint4*>(p.layers);
-    for (int k = threadIdx.x; k < p.L * 4; k += WARPS * 32) dst[k] = src[k];
+    for (int k = threadIdx.x; k < p.L * 4; k += (WARPS + 2) * 32) dst[k] = src[k];
     lys = lys_s;
   }
-  if (threadIdx.x < step_seg_bufs(WARPS) * 4)
-    reinterpret_cast<unsigned*>(segbuf + (threadIdx.x >> 2) * kSegBufFloats + WARPS * D + WARPS * 2)[threadIdx.x & 3] = 0u;
-  if (lane == 0 && warp < WARPS) {
-#pragma unroll
-    for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
-    fence_mbar_init();
-  }
-  if (threadIdx.x < 2) { cta_ctl[threadIdx.x] = 0u; mail_ctl[threadIdx.x] = 0u; }
-  if (COMM && threadIdx.x < kMailSlots) mail_state[threadIdx.x] = 0u;
-  __syncthreads();
-
-  const unsigned epoch = *reinterpret_cast<volatile const unsigned*>(p.ctrl);
-  const unsigned flag_target = (epoch + 1u) * p.rows;
-  const int G = gridDim.x;
-
-  if (COMM && warp == WARPS) {
-    // ---- communication warp: serve the mailbox in claim order until every compute warp has finished ------------------
-    volatile unsigned* mstate = mail_state;
-    volatile unsigned* mctl = mail_ctl;
-    unsigned next = 0;
-    while (true) {
-      const unsigned slot = next % kMailSlots, want = 2u * (next / kMailSlots) + 1u;
-      bool have = false;
-      while (true) {
-        if (mstate[slot] == want) { have = true; break; }
-        if (mctl[1] == static_cast<unsigned>(WARPS) && mctl[0] == next) break;
-        __nanosleep(100);
-      }
-      if (!have) break;
-      __threadfence_block();
-      const int layer = mail_meta[slot][0], row = mail_meta[slot][1];
-      const int64_t off = static_cast<int64_t>(layer) * p.peer_layer_stride + static_cast<int64_t>(row) * D + lane * PER;
-      if (PER == 4) {
-        const uint2 v = *reinterpret_cast<const uint2*>(&mail_row[slot][lane * PER]);
-#pragma unroll 1
-        for (int r = 0; r < p.n_out; ++r) *reinterpret_cast<uint2*>(p.peer_out[r] + off) = v;
-      } else {
-        const uint32_t v = *reinterpret_cast<const uint32_t*>(&mail_row[slot][lane * PER]);
-#pragma unroll 1
-        for (int r = 0; r < p.n_out; ++r) *reinterpret_cast<uint32_t*>(p.peer_out[r] + off) = v;
-      }
-      __syncwarp();
-      if (lane < p.n_flag) {
-        unsigned int* f = p.flag_ptr[lane] + static_cast<int64_t>(layer) * p.flag_layer_stride;
-        asm volatile("fence.acq_rel.sys;\n\tred.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(f) : "memory");
-      }
-      __syncwarp();
-      if (lane == 0) mstate[slot] = want + 1u;          // free for the next generation
-      ++next;
-    }
-  } else {
-
-  // ---- work split: layer l's tile list is cut into G contiguous CTA ranges; inside a CTA, warp w takes the tiles at
-  //      range positions w, w + WARPS, ... -- so the 8/16 warps of an SM work on neighbouring tiles of (mostly) one row
-  //      at the same time and their partials are combined on chip before anything goes to global memory ------------
-  auto layer_range = [&](int l) {
-    LayerRange r;
+  auto compute_range = [&](int l) {                            // warp-uniform (ballots)
+    RangeRec r;
     r.cs = r.ce = 0; r.nlh = p.H; r.hm = ~0ull; r.vcta = 0; r.T = 0; r.geff = 1;
-    if (l >= p.L) return r;
     if (p.head_mask) {
       const uint8_t* hr = p.head_mask + static_cast<size_t>(l) * p.H;
       const unsigned lo = __ballot_sync(0xffffffffu, lane < p.H && hr[lane] != 0);
@@ -238,503 +192,243 @@ __global__ void __launch_bounds__((WARPS + (COMM ? 1 : 0)) * 32, 1) decode_step_
     }
     return r;
   };
+  const bool ranges_in_smem = p.L <= kStepSmemLayers;
+  if (ranges_in_smem) {
+    for (int l = warp; l < p.L; l += WARPS + 2) {
+      const RangeRec r = compute_range(l);
+      if (lane == 0) ranges[l] = r;
+    }
+  }
+  if (threadIdx.x < NB * 4) seg_ctl[threadIdx.x >> 2][threadIdx.x & 3] = 0u;
+  if (lane == 0 && warp < WARPS) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto layer_range = [&](int l) -> RangeRec { return ranges_in_smem ? ranges[l] : compute_range(l); };
   auto row_coords = [&](int i, int nlh, unsigned long long hm, int& bi, int& h) {
     bi = i / nlh;
     const int hidx = i - bi * nlh;
     h = p.head_mask ? nth_set_bit64(hm, hidx) : hidx;
   };
 
-  // ---- issue side: this warp's tile sequence, STAGES tiles ahead of the consumer, walking on across layers ----------
-  const uint64_t pol = policy_evict_first();
-  int il = 0, ik = 0, ike = 0;                   // layer, tile in the layer's list, end of the CTA's range
-  int ii = 0, ij = 0;                            // row and tile-in-row of tile ik
-  bool irow_new = true;                          // the pointers below have to be recomputed
-  int inlh = p.H;
-  unsigned long long ihm = ~0ull;
-  const __half* ikp = nullptr;                   // K / V address of row ii, tile 0
-  const __half* ivp = nullptr;
-  // this warp's tiles of layer l: range positions (warp + l) % WARPS, + WARPS, ... (the offset rotates with the layer so
-  // that the warps taking one tile more than the others change from layer to layer)
-  auto issue_enter = [&](int l) {
-    const LayerRange r = layer_range(l);
-    ik = r.cs + (warp + l) % WARPS; ike = r.ce; inlh = r.nlh; ihm = r.hm;
-    if (ik < ike) { ii = ik / p.tpr; ij = ik - ii * p.tpr; irow_new = true; }
-  };
-  auto issue_seek = [&]() {                      // make (il, ik) name this warp's next tile, or il = L
-    while (il < p.L && ik >= ike) {
-      ++il;
-      if (il < p.L) issue_enter(il);
-    }
-  };
-  issue_enter(0);
-  issue_seek();
-  auto issue_next = [&](int s) {                 // copy the issue cursor's tile into stage s, move the cursor on
-    if (il >= p.L) return;
-    if (irow_new) {
-      int bi, h;
-      row_coords(ii, inlh, ihm, bi, h);
-      const SpattenStepLayer* ly = lys + il;
-      const int64_t off = bi * p.stride_b + (h / p.n_rep) * p.stride_h;
-      ikp = static_cast<const __half*>(ly->k_cache) + off;
-      ivp = static_cast<const __half*>(ly->v_cache) + off;
-      irow_new = false;
-    }
-    const int ncopy = min(kTile, p.kv_len - ij * kTile);
-    if (ncopy > 0)
-      issue_kv_copies(lane == 0, wsm_u32 + s * kStageBytes, wsm_u32 + s * kStageBytes + kTileBytes,
-                      ikp + static_cast<int64_t>(ij) * (kTile * D), ivp + static_cast<int64_t>(ij) * (kTile * D),
-                      static_cast<uint32_t>(ncopy) * kRowBytes, bars_u32 + s * 8, pol);
-    ik += WARPS; ij += WARPS;
-    while (ij >= p.tpr) { ij -= p.tpr; ++ii; irow_new = true; }
-    if (ik >= ike) issue_seek();
-  };
-
-  // RoPE rows of one tile: cos | sin for the passes of this lane's key group (L2 resident table)
-  auto load_table = [&](int tok0, HV (&cs)[PASSES], HV (&sn)[PASSES]) {
-    if (tok0 + kTile <= p.rope_len) {
-      const __half* r = p.rope + static_cast<int64_t>(tok0 + g) * D + c * E2;
-#pragma unroll
-      for (int ps = 0; ps < PASSES; ++ps) {
-        *reinterpret_cast<Vec*>(&cs[ps]) = __ldg(reinterpret_cast<const Vec*>(r + ps * 4 * D));
-        *reinterpret_cast<Vec*>(&sn[ps]) = __ldg(reinterpret_cast<const Vec*>(r + ps * 4 * D + D / 2));
-      }
-    } else {
-#pragma unroll
-      for (int ps = 0; ps < PASSES; ++ps) {
-        const int j = min(tok0 + ps * 4 + g, p.rope_len - 1);
-        const __half* r = p.rope + static_cast<int64_t>(j) * D + c * E2;
-        *reinterpret_cast<Vec*>(&cs[ps]) = __ldg(reinterpret_cast<const Vec*>(r));
-        *reinterpret_cast<Vec*>(&sn[ps]) = __ldg(reinterpret_cast<const Vec*>(r + D / 2));
-      }
-    }
-  };
+  const unsigned epoch = *reinterpret_cast<volatile const unsigned*>(p.ctrl);
+  const unsigned flag_target = (epoch + 1u) * p.rows;
 
   // wait until every producer's flag of `layer` has reached this step's target (relaxed polls, one acquire fence)
-  // One warp per CTA polls the global flags (relaxed loads, one acquire fence) and tells the others through shared
-  // memory: 148 pollers on the flag's L2 line instead of every warp of the grid.
   auto wait_layer = [&](int layer) {
-    volatile unsigned* seen = cta_ctl;               // layers [0, *seen) are known complete
-    if (*seen <= static_cast<unsigned>(layer)) {
-      unsigned mine = 0;
-      if (lane == 0) mine = atomicMax(cta_ctl + 1, static_cast<unsigned>(layer) + 1u) <= static_cast<unsigned>(layer);
-      mine = __shfl_sync(0xffffffffu, mine, 0);
-      if (mine) {
-        if (lane < p.wait_n) {
-          const unsigned* f = p.wait_flags + static_cast<int64_t>(layer) * p.wait_n + lane;
-          const long long tw = clock64();
-          while (static_cast<int>(ld_relaxed(f, p.sys_scope) - flag_target) < 0) {
-            if (clock64() - tw > 4000000000ll) { atomicExch(p.ctrl + 2, 1u); break; }   // ~2 s: never wedge the GPU
-          }
+    if (lane < p.wait_n) {
+      const unsigned* f = p.wait_flags + static_cast<int64_t>(layer) * p.wait_n + lane;
+      const long long tw = clock64();
+      while (static_cast<int>(ld_relaxed(f, p.sys_scope) - flag_target) < 0) {
+        if (clock64() - tw > 4000000000ll) { atomicExch(p.ctrl + 2, 1u); break; }   // ~2 s: never wedge the GPU
+        __nanosleep(20);
+      }
+    }
+    __syncwarp();
+    if (p.sys_scope) asm volatile("fence.acq_rel.sys;" ::: "memory");
+    else asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  };
+  auto seg_part = [&](unsigned seq) { return segbuf + (seq % NB) * kSegBufFloats; };
+  auto seg_ml = [&](unsigned seq) { return reinterpret_cast<float2*>(seg_part(seq) + WARPS * D); };
+  auto seg_q = [&](unsigned seq) { return reinterpret_cast<__half*>(seg_part(seq) + WARPS * D + WARPS * 2); };
+
+  if (warp == WARPS) {
+    // ================= QUERY warp: rotate the query of every segment of this CTA into shared memory, in order ==========
+    unsigned seq = 0;
+#pragma unroll 1
+    for (int l = 0; l < p.L; ++l) {
+      const RangeRec R = layer_range(l);
+      if (R.cs >= R.ce) continue;
+      const SpattenStepLayer* ly = lys + l;
+      // the decoder's dependency: layer l's query exists only when every row of layer l-1 has been stored
+      if (l > 0 && p.chain) wait_layer(l - 1);
+      STAMP(l, 1);
+      const int i0 = R.cs / p.tpr, i1 = (R.ce - 1) / p.tpr;
+#pragma unroll 1
+      for (int i = i0; i <= i1; ++i, ++seq) {
+        volatile unsigned* ctl = seg_ctl[seq % NB];
+        const unsigned use = seq / NB;
+        while (ctl[1] != use) __nanosleep(40);               // the buffer's previous segment has been combined
+        int bi, h;
+        row_coords(i, R.nlh, R.hm, bi, h);
+        const int row = bi * p.H + h;
+        int64_t pos = p.q_pos ? p.q_pos[bi] : p.kv_len;
+        pos = max(static_cast<int64_t>(0), min(pos, static_cast<int64_t>(p.rope_len - 1)));
+        // lane t rotates dims {2t, 2t+1} (D = 128) of the lower half with their partners in the upper half (:21-28, fp16)
+        if (lane < D / 4) {
+          const __half* qr = static_cast<const __half*>(ly->q) + static_cast<int64_t>(row) * D;
+          const __half2 qa = *reinterpret_cast<const __half2*>(qr + 2 * lane);
+          const __half2 qb = *reinterpret_cast<const __half2*>(qr + D / 2 + 2 * lane);
+          const __half2 cs = *reinterpret_cast<const __half2*>(p.rope + pos * D + 2 * lane);
+          const __half2 sn = *reinterpret_cast<const __half2*>(p.rope + pos * D + D / 2 + 2 * lane);
+          __half* qs = seg_q(seq);
+          *reinterpret_cast<__half2*>(qs + 2 * lane) = __hsub2_rn(__hmul2_rn(qa, cs), __hmul2_rn(qb, sn));
+          *reinterpret_cast<__half2*>(qs + D / 2 + 2 * lane) = __hadd2_rn(__hmul2_rn(qb, cs), __hmul2_rn(qa, sn));
         }
         __syncwarp();
-        if (p.sys_scope) asm volatile("fence.acq_rel.sys;" ::: "memory");
-        else asm volatile("fence.acq_rel.gpu;" ::: "memory");
-        if (lane == 0) atomicMax(cta_ctl, static_cast<unsigned>(layer) + 1u);
-      } else {
-        while (*seen <= static_cast<unsigned>(layer)) __nanosleep(20);
+        if (lane == 0) {
+          __threadfence_block();
+          ctl[2] = use + 1;                                    // query of segment `seq` is in shared memory
+        }
       }
     }
-    __threadfence_block();
-  };
-
-  // every lane stored its piece of a row of layer `layer`: publish it
-  auto signal_row = [&](int layer) {
-    if (p.n_flag == 0 || (COMM && p.n_out > 0)) return;      // COMM: the communication warp publishes the row
-    __syncwarp();
-    if (lane < p.n_flag) {
-      unsigned int* f = p.flag_ptr[lane] + static_cast<int64_t>(layer) * p.flag_layer_stride;
-      if (p.sys_scope) asm volatile("fence.acq_rel.sys;\n\tred.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(f) : "memory");
-      else asm volatile("fence.acq_rel.gpu;\n\tred.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(f) : "memory");
-    }
-  };
-
-  // lane owns dims [lane*PER, lane*PER + PER) of the finished row: normalise, round, store (locally or to every peer)
-  auto emit_row = [&](int layer, int row, const float (&o)[PER], float inv, float M) {
-    __half oh16[PER];
-    float habs = 0.f;
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-      oh16[k] = __float2half_rn(o[k] * inv);
-      habs += fabsf(__half2float(oh16[k]));
-    }
-    const int64_t off = static_cast<int64_t>(row) * D + lane * PER;
-    if (p.n_out == 0) {
-      __half* dst = static_cast<__half*>(lys[layer].out) + off;
-      if (PER == 4) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(oh16);
-      else *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(oh16);
-    } else if (COMM) {
-      // hand the row to the communication warp: claim a mailbox slot, wait until its previous use has been sent
-      unsigned claim = 0;
-      if (lane == 0) claim = atomicAdd(&mail_ctl[0], 1u);
-      claim = __shfl_sync(0xffffffffu, claim, 0);
-      const unsigned slot = claim % kMailSlots, gen = 2u * (claim / kMailSlots);
-      while (*reinterpret_cast<volatile unsigned*>(&mail_state[slot]) != gen) __nanosleep(40);
-      if (PER == 4) *reinterpret_cast<uint2*>(&mail_row[slot][lane * PER]) = *reinterpret_cast<const uint2*>(oh16);
-      else *reinterpret_cast<uint32_t*>(&mail_row[slot][lane * PER]) = *reinterpret_cast<const uint32_t*>(oh16);
-      if (lane == 0) { mail_meta[slot][0] = layer; mail_meta[slot][1] = row; }
+  } else if (warp == WARPS + 1) {
+    // ================= MERGE warp: combine finished segments, publish, merge rows, store, signal ======================
+    // every lane stored its piece of a row of layer `layer`: publish it to the consumers of the flags
+    auto signal_row = [&](int layer) {
+      if (p.n_flag == 0) return;
       __syncwarp();
-      if (lane == 0) {
-        __threadfence_block();
-        *reinterpret_cast<volatile unsigned*>(&mail_state[slot]) = gen + 1u;
+      if (lane < p.n_flag) {
+        unsigned int* f = p.flag_ptr[lane] + static_cast<int64_t>(layer) * p.flag_layer_stride;
+        if (p.sys_scope) asm volatile("fence.acq_rel.sys;\n\tred.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(f) : "memory");
+        else asm volatile("fence.acq_rel.gpu;\n\tred.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(f) : "memory");
       }
-    } else {
-#pragma unroll 1
-      for (int r = 0; r < p.n_out; ++r) {
-        __half* dst = p.peer_out[r] + static_cast<int64_t>(layer) * p.peer_layer_stride + off;
+    };
+    // lane owns dims [lane*PER, lane*PER + PER) of the finished row: normalise, round, store (locally or to every peer)
+    auto emit_row = [&](int layer, int row, const float (&o)[PER], float inv, float M) {
+      __half oh16[PER];
+      float habs = 0.f;
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        oh16[k] = __float2half_rn(o[k] * inv);
+        habs += fabsf(__half2float(oh16[k]));
+      }
+      const int64_t off = static_cast<int64_t>(row) * D + lane * PER;
+      if (p.n_out == 0) {
+        __half* dst = static_cast<__half*>(lys[layer].out) + off;
         if (PER == 4) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(oh16);
         else *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(oh16);
-      }
-    }
-    if (p.head_importance) {
-      habs = warp_sum(habs);
-      if (lane == 0) atomicAdd(p.head_importance + row % p.H, habs);
-    }
-    const SpattenStepLayer* ly = lys + layer;
-    if (ly->importance && ly->logits && M > -CUDART_INF_F) {
-      const unsigned short* lgr = reinterpret_cast<const unsigned short*>(
-          static_cast<const __half*>(ly->logits) + static_cast<int64_t>(row) * p.logits_stride);
-      float* imp = ly->importance + static_cast<int64_t>(row) * p.imp_stride;
+      } else {
 #pragma unroll 1
-      for (int j = lane; j < p.n_total; j += 32) {
-        const __half s16 = __ushort_as_half(__ldcg(lgr + j));
-        imp[j] += fast_exp2((__half2float(s16) - M) * kLog2e) * inv;
-      }
-    }
-    signal_row(layer);
-  };
-
-  // pruned heads of a layer: zero their output rows, keep the KV cache complete, count them as done
-  auto dead_rows = [&](int layer, const LayerRange& R) {
-    const SpattenStepLayer* ly = lys + layer;
-    const int ndh = p.H - R.nlh, n_dead = p.b * ndh;
-    if (static_cast<unsigned>(R.vcta) >= R.geff) return;       // CTAs without a range in this layer take no rows either
-    const int vw = R.vcta * WARPS + warp, nvw = static_cast<int>(R.geff) * WARPS;
-    const unsigned long long hall = p.H >= 64 ? ~0ull : ((1ull << p.H) - 1ull);
-#pragma unroll 1
-    for (int dr = vw; dr < n_dead; dr += nvw) {
-      const int dbi = dr / ndh;
-      const int dh = nth_set_bit64(~R.hm & hall, dr - dbi * ndh);
-      const int dkvh = dh / p.n_rep;
-      const unsigned long long grp = (R.hm >> (dkvh * p.n_rep)) & (p.n_rep >= 64 ? ~0ull : ((1ull << p.n_rep) - 1ull));
-      if (p.append && grp == 0 && dh == dkvh * p.n_rep) {
-        constexpr int kChunks = kRowBytes / 16;
-        const int which = lane / kChunks, ch = lane % kChunks;
-#pragma unroll 1
-        for (int w = which; w < 2; w += 32 / kChunks) {
-          const __half* src = static_cast<const __half*>(w ? ly->v_new : ly->k_new) +
-                              (static_cast<int64_t>(dbi) * p.H_kv + dkvh) * D + ch * 8;
-          __half* dst = static_cast<__half*>(w ? ly->v_cache : ly->k_cache) + dbi * p.stride_b + dkvh * p.stride_h +
-                        static_cast<int64_t>(p.kv_len) * D + ch * 8;
-          *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+        for (int r = 0; r < p.n_out; ++r) {
+          __half* dst = p.peer_out[r] + static_cast<int64_t>(layer) * p.peer_layer_stride + off;
+          if (PER == 4) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(oh16);
+          else *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(oh16);
         }
       }
-      float z[PER];
-#pragma unroll
-      for (int k = 0; k < PER; ++k) z[k] = 0.f;
-      emit_row(layer, dbi * p.H + dh, z, 0.f, -CUDART_INF_F);
-    }
-  };
-
-  // ---- pipeline prologue ----------------------------------------------------------------------------------------
+      if (p.head_importance) {
+        habs = warp_sum(habs);
+        if (lane == 0) atomicAdd(p.head_importance + row % p.H, habs);
+      }
+      const SpattenStepLayer* ly = lys + layer;
+      if (ly->importance && ly->logits && M > -CUDART_INF_F) {
+        const unsigned short* lgr = reinterpret_cast<const unsigned short*>(
+            static_cast<const __half*>(ly->logits) + static_cast<int64_t>(row) * p.logits_stride);
+        float* imp = ly->importance + static_cast<int64_t>(row) * p.imp_stride;
 #pragma unroll 1
-  for (int s = 0; s < STAGES; ++s) issue_next(s);
-
-  unsigned phase = 0;     // bit s = parity the next wait on stage s uses
-  int s = 0;
-  unsigned seg_seq = 0;   // segments (CTA range x row) this CTA has walked past: selects the shared-memory buffer
-
-#pragma unroll 1
-  for (int l = 0; l < p.L; ++l) {
-    const LayerRange R = layer_range(l);
-    const SpattenStepLayer* ly = lys + l;
-    bool waited = !(l > 0 && p.chain);
-    if (p.head_mask && R.nlh < p.H && R.T > 0) {
-      // the appended rows of fully pruned kv groups come from this layer's projections: same dependency as the query
-      if (!waited) { wait_layer(l - 1); waited = true; }
-      dead_rows(l, R);
-    }
-    if (R.cs >= R.ce) continue;
-    const int i0 = R.cs / p.tpr, i1 = (R.ce - 1) / p.tpr;
-    int k = R.cs + (warp + l) % WARPS;                     // this warp's next tile in the layer's list
-
-#pragma unroll 1
-    for (int i = i0; i <= i1; ++i, ++seg_seq) {
-      // ---- one segment: the part of row i inside this CTA's range; this warp's tiles of it --------------------------
-      const int row_end = min(R.ce, (i + 1) * p.tpr);
-      const bool have = k < row_end;
-      int bi, h;
-      row_coords(i, R.nlh, R.hm, bi, h);
-      const int row = bi * p.H + h;
-      float fin[PER];
-      float m = -CUDART_INF_F, lsum = 0.f;
-      if (have) {
-        // the decoder's dependency: layer l's query exists only when every row of layer l-1 has been stored
-        STAMP(l, 0);                                       // segment reached
-        if (!waited) { wait_layer(l - 1); waited = true; }
-        STAMP(l, 1);                                       // previous layer complete (chain)
-        int j = k - i * p.tpr;
-        HV cs[PASSES], sn[PASSES];
-        load_table(j * kTile, cs, sn);
-        // query of this row, rotated at its position id (modify_llama.py:92), fp16 op-for-op, kept as fp32
-        HV qlr, qhr;                                      // rotated query, exactly the fp16 values the reference forms
-        float accl[E2], acch[E2];
-        {
-          int64_t pos = p.q_pos ? p.q_pos[bi] : p.kv_len;
-          pos = max(static_cast<int64_t>(0), min(pos, static_cast<int64_t>(p.rope_len - 1)));
-          const __half* qr = static_cast<const __half*>(ly->q) + static_cast<int64_t>(row) * D;
-          HV qa, qb, qcs, qsn;
-          *reinterpret_cast<Vec*>(&qa) = *reinterpret_cast<const Vec*>(qr + c * E2);
-          *reinterpret_cast<Vec*>(&qb) = *reinterpret_cast<const Vec*>(qr + D / 2 + c * E2);
-          *reinterpret_cast<Vec*>(&qcs) = __ldg(reinterpret_cast<const Vec*>(p.rope + pos * D + c * E2));
-          *reinterpret_cast<Vec*>(&qsn) = __ldg(reinterpret_cast<const Vec*>(p.rope + pos * D + D / 2 + c * E2));
-#pragma unroll
-          for (int e = 0; e < NH2; ++e) {
-            qlr.h[e] = __hsub2_rn(__hmul2_rn(qa.h[e], qcs.h[e]), __hmul2_rn(qb.h[e], qsn.h[e]));
-            qhr.h[e] = __hadd2_rn(__hmul2_rn(qb.h[e], qcs.h[e]), __hmul2_rn(qa.h[e], qsn.h[e]));
-          }
+        for (int j = lane; j < p.n_total; j += 32) {
+          const __half s16 = __ushort_as_half(__ldcg(lgr + j));
+          imp[j] += fast_exp2((__half2float(s16) - M) * kLog2e) * inv;
         }
-#pragma unroll
-        for (int e = 0; e < E2; ++e) accl[e] = acch[e] = 0.f;
-        const int kvh = h / p.n_rep;
-        bool writer = (h % p.n_rep) == 0;
-        if (p.head_mask) {
-          const unsigned long long grp = (R.hm >> (kvh * p.n_rep)) & (p.n_rep >= 64 ? ~0ull : ((1ull << p.n_rep) - 1ull));
-          writer = h == kvh * p.n_rep + (__ffsll(static_cast<long long>(grp)) - 1);   // first live head of the kv group
-        }
-        __half* lg = ly->logits ? static_cast<__half*>(ly->logits) + static_cast<int64_t>(row) * p.logits_stride : nullptr;
-
+      }
+      signal_row(layer);
+    };
+    unsigned seq = 0;
 #pragma unroll 1
-        for (; k < row_end; k += WARPS, j += WARPS) {
-          // ---- one tile ---------------------------------------------------------------------------------------------
-          const int tok0 = j * kTile;
-          const int ntok = min(kTile, p.n_total - tok0);           // valid tokens (incl. the appended one)
-          const int ncopy = max(0, min(kTile, p.kv_len - tok0));   // of which bulk-copied from the cache
-          uint8_t* Ks = wsm + s * kStageBytes;
-          uint8_t* Vs = Ks + kTileBytes;
-
-          const bool generic_writes = ntok < kTile;                // only the last tile of a row
-          if (generic_writes) {
-            // zero the rows the copy does not write, so masked lanes multiply finite numbers
+    for (int l = 0; l < p.L; ++l) {
+      const RangeRec R = layer_range(l);
+      const SpattenStepLayer* ly = lys + l;
+      if (p.head_mask && R.nlh < p.H && R.T > 0 && static_cast<unsigned>(R.vcta) < R.geff) {
+        // pruned heads of the layer: zero their output rows, keep the KV cache complete, count them as done.  The appended
+        // rows of fully pruned kv groups come from this layer's projections: same dependency as the query.
+        if (l > 0 && p.chain) wait_layer(l - 1);
+        const int ndh = p.H - R.nlh, n_dead = p.b * ndh;
+        const unsigned long long hall = p.H >= 64 ? ~0ull : ((1ull << p.H) - 1ull);
 #pragma unroll 1
-            for (int o = ncopy * kRowBytes + lane * 16; o < kTileBytes; o += 32 * 16) {
-              *reinterpret_cast<uint4*>(Ks + o) = make_uint4(0, 0, 0, 0);
-              *reinterpret_cast<uint4*>(Vs + o) = make_uint4(0, 0, 0, 0);
-            }
-            __syncwarp();
-          }
-          if (ncopy > 0) {
-            if (!mbar_try_wait(&bars[s], (phase >> s) & 1u)) {
-              const long long tw = clock64();
-              while (!mbar_try_wait(&bars[s], (phase >> s) & 1u)) {
-                if (clock64() - tw > 4000000000ll) __trap();    // a lost copy must fail the launch, not wedge the GPU
-              }
-            }
-            phase ^= 1u << s;
-          }
-          if (DBG && k == R.cs + (warp + l) % WARPS) STAMP(l, 2);   // first tile of the layer landed, query rotated
-          if (ncopy < ntok) {
-            // the appended token (modify_llama.py:95-100): its un-rotated K/V row goes into the tile and into slot kv_len
+        for (int dr = R.vcta; dr < n_dead; dr += static_cast<int>(R.geff)) {
+          const int dbi = dr / ndh;
+          const int dh = nth_set_bit64(~R.hm & hall, dr - dbi * ndh);
+          const int dkvh = dh / p.n_rep;
+          const unsigned long long grp = (R.hm >> (dkvh * p.n_rep)) & (p.n_rep >= 64 ? ~0ull : ((1ull << p.n_rep) - 1ull));
+          if (p.append && grp == 0 && dh == dkvh * p.n_rep) {
             constexpr int kChunks = kRowBytes / 16;
-            const int r = p.kv_len - tok0;
             const int which = lane / kChunks, ch = lane % kChunks;
 #pragma unroll 1
             for (int w = which; w < 2; w += 32 / kChunks) {
               const __half* src = static_cast<const __half*>(w ? ly->v_new : ly->k_new) +
-                                  (static_cast<int64_t>(bi) * p.H_kv + kvh) * D + ch * 8;
-              const uint4 val = *reinterpret_cast<const uint4*>(src);
-              *reinterpret_cast<uint4*>((w ? Vs : Ks) + r * kRowBytes + ch * 16) = val;
-              if (writer) {
-                __half* dst = static_cast<__half*>(w ? ly->v_cache : ly->k_cache) + bi * p.stride_b + kvh * p.stride_h +
-                              static_cast<int64_t>(p.kv_len) * D + ch * 8;
-                *reinterpret_cast<uint4*>(dst) = val;
-              }
-            }
-            __syncwarp();
-          }
-
-          // scores of the tile: rotated key rounded to fp16 after every elementwise op (:27), products summed in fp32
-          float d[PASSES];
-#pragma unroll
-          for (int ps = 0; ps < PASSES; ++ps) {
-            const int tl = ps * 4 + g;
-            HV kl, kh;
-            *reinterpret_cast<Vec*>(&kl) = *reinterpret_cast<const Vec*>(Ks + tl * kRowBytes + c * VB);
-            *reinterpret_cast<Vec*>(&kh) = *reinterpret_cast<const Vec*>(Ks + tl * kRowBytes + D + c * VB);
-            float d0 = 0.f, d1 = 0.f;
-#pragma unroll
-            for (int e = 0; e < NH2; ++e) {
-              const __half2 rl = __hsub2_rn(__hmul2_rn(kl.h[e], cs[ps].h[e]), __hmul2_rn(kh.h[e], sn[ps].h[e]));
-              const __half2 rh = __hadd2_rn(__hmul2_rn(kh.h[e], cs[ps].h[e]), __hmul2_rn(kl.h[e], sn[ps].h[e]));
-              d0 = fhfma_lo(rl, qlr.h[e], d0);             // fp16 x fp16 products are exact in fp32 (FHFMA): same sums
-              d0 = fhfma_hi(rl, qlr.h[e], d0);             // as fmaf(float(q), float(k), d) without the conversions
-              d1 = fhfma_lo(rh, qhr.h[e], d1);
-              d1 = fhfma_hi(rh, qhr.h[e], d1);
-            }
-            d[ps] = d0 + d1;
-          }
-          // the RoPE registers are free: fetch the rows of this warp's next tile of the segment under the rest of this one
-          if (k + WARPS < row_end) load_table((j + WARPS) * kTile, cs, sn);
-
-#pragma unroll
-          for (int o = 1; o <= 4; o <<= 1) {
-#pragma unroll
-            for (int ps = 0; ps < PASSES; ++ps) d[ps] += __shfl_xor_sync(0xffffffffu, d[ps], o);
-          }
-          // fp16 logit exactly as the reference forms it: fp16(matmul) / sqrt(D) -> fp16 (:111-113)
-          float sc[PASSES];
-          float mx = -CUDART_INF_F;
-#pragma unroll
-          for (int ps = 0; ps < PASSES; ++ps) {
-            const int tl = ps * 4 + g;
-            const bool valid = tl < ntok;
-            const __half s16 = __float2half_rn(div_by_const(__half2float(__float2half_rn(d[ps])), p.sqrt_d, p.rsqrt_d));
-            if (valid && c == 0 && lg) lg[tok0 + tl] = s16;
-            sc[ps] = valid ? __half2float(s16) : -CUDART_INF_F;
-            mx = fmaxf(mx, sc[ps]);
-          }
-          // online softmax (:135): m is warp-uniform; l and acc are per key group until the segment ends
-          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
-          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
-          const float m_new = fmaxf(m, mx);
-          if (m_new > -CUDART_INF_F) {
-            if (m_new != m) {
-              const float corr = fast_exp2((m - m_new) * kLog2e);
-              lsum *= corr;
-#pragma unroll
-              for (int e = 0; e < E2; ++e) { accl[e] *= corr; acch[e] *= corr; }
-              m = m_new;
-            }
-            // the probabilities enter P.V as fp16, as in the reference (softmax(...).to(fp16) @ V, :135-138); the running
-            // sum uses the same rounded values, so the final normalisation is exact for what was accumulated
-            __half2 ph[PASSES];
-#pragma unroll
-            for (int ps = 0; ps < PASSES; ++ps) {
-              ph[ps] = __float2half2_rn(fast_exp2((sc[ps] - m) * kLog2e));
-              lsum += __low2float(ph[ps]);
-            }
-            // P.V (:138)
-#pragma unroll
-            for (int ps = 0; ps < PASSES; ++ps) {
-              const int tl = ps * 4 + g;
-              HV vl, vh;
-              *reinterpret_cast<Vec*>(&vl) = *reinterpret_cast<const Vec*>(Vs + tl * kRowBytes + c * VB);
-              *reinterpret_cast<Vec*>(&vh) = *reinterpret_cast<const Vec*>(Vs + tl * kRowBytes + D + c * VB);
-#pragma unroll
-              for (int e = 0; e < NH2; ++e) {
-                accl[2 * e] = fhfma_lo(vl.h[e], ph[ps], accl[2 * e]);
-                accl[2 * e + 1] = fhfma_hi(vl.h[e], ph[ps], accl[2 * e + 1]);
-                acch[2 * e] = fhfma_lo(vh.h[e], ph[ps], acch[2 * e]);
-                acch[2 * e + 1] = fhfma_hi(vh.h[e], ph[ps], acch[2 * e + 1]);
-              }
+                                  (static_cast<int64_t>(dbi) * p.H_kv + dkvh) * D + ch * 8;
+              __half* dst = static_cast<__half*>(w ? ly->v_cache : ly->k_cache) + dbi * p.stride_b + dkvh * p.stride_h +
+                            static_cast<int64_t>(p.kv_len) * D + ch * 8;
+              *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
             }
           }
-
-          // stage s is free: refill it with this warp's tile STAGES ahead (possibly the next layer's)
-          if (generic_writes) fence_proxy_async();         // generic-proxy writes above vs the async-proxy copy below
-          __syncwarp();
-          issue_next(s);
-          s = (s + 1 == STAGES) ? 0 : s + 1;
-        }
-
-        STAMP(l, 3);                                       // tiles done
-        // ---- this warp's tiles of the segment are done: reduce-scatter over the 4 key groups (lane bits 3 and 4) -----
-        lsum += __shfl_xor_sync(0xffffffffu, lsum, 8);
-        lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
-        float keep[E2];
-        const bool up = (g & 1) != 0;                 // bit 3: keep the upper half-row, send the lower
+          float z[PER];
 #pragma unroll
-        for (int e = 0; e < E2; ++e) {
-          const float send = up ? accl[e] : acch[e];
-          const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
-          keep[e] = (up ? acch[e] : accl[e]) + recv;
-        }
-        const bool up2 = (g & 2) != 0;                // bit 4: keep the upper PER of the E2 values
-#pragma unroll
-        for (int e = 0; e < PER; ++e) {
-          const float send = up2 ? keep[e] : keep[e + PER];
-          const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
-          fin[e] = (up2 ? keep[e + PER] : keep[e]) + recv;
+          for (int k = 0; k < PER; ++k) z[k] = 0.f;
+          emit_row(l, dbi * p.H + dh, z, 0.f, -CUDART_INF_F);
         }
       }
-
-      // ---- CTA level: every warp checks in at the segment's shared-memory buffer; the last one combines ------------
-      float* sb = segbuf + (seg_seq % step_seg_bufs(WARPS)) * kSegBufFloats;
-      float2* sml = reinterpret_cast<float2*>(sb + WARPS * D);
-      volatile unsigned* sctl = reinterpret_cast<volatile unsigned*>(sb + WARPS * D + WARPS * 2);   // [0] arrivals, [1] uses done
-      const unsigned use = seg_seq / step_seg_bufs(WARPS);
-      while (sctl[1] != use) __nanosleep(40);                 // the buffer's previous segment has been combined
-      if (have) {
-        const int d0 = (g & 1) * (D / 2) + c * E2 + (g >> 1) * PER;   // first of the PER dims this lane owns
-        *reinterpret_cast<PV_t*>(sb + warp * D + d0) = *reinterpret_cast<const PV_t*>(fin);
-      }
-      if (lane == 0) sml[warp] = make_float2(m, lsum);
-      __syncwarp();
-      unsigned arrived = 0;
-      if (lane == 0) {
+      if (R.cs >= R.ce) continue;
+      const int i0 = R.cs / p.tpr, i1 = (R.ce - 1) / p.tpr;
+#pragma unroll 1
+      for (int i = i0; i <= i1; ++i, ++seq) {
+        volatile unsigned* ctl = seg_ctl[seq % NB];
+        const unsigned use = seq / NB;
+        while (ctl[0] != static_cast<unsigned>(WARPS)) __nanosleep(40);      // every compute warp has checked in
         __threadfence_block();
-        arrived = atomicAdd(const_cast<unsigned*>(&sctl[0]), 1u);
-      }
-      arrived = __shfl_sync(0xffffffffu, arrived, 0);
-      if (arrived != WARPS - 1) continue;
-      __threadfence_block();
-      STAMP(l, 4);                                         // last of the CTA: combining
-
-      // last warp of the CTA at this segment: combine the WARPS partials on chip
-      float M, Lsum;
-      float o[PER];
-      {
-        const float2 mlj = lane < WARPS ? sml[lane] : make_float2(-CUDART_INF_F, 0.f);
-        M = warp_max(mlj.x);
-        const float wj = (M > -CUDART_INF_F && lane < WARPS) ? fast_exp2((mlj.x - M) * kLog2e) : 0.f;
-        Lsum = warp_sum(mlj.y * wj);
+        STAMP(l, 4);
+        const float* sb = seg_part(seq);
+        const float2* sml = seg_ml(seq);
+        int bi, h;
+        row_coords(i, R.nlh, R.hm, bi, h);
+        const int row = bi * p.H + h;
+        float M, Lsum;
+        float o[PER];
+        {
+          const float2 mlj = lane < WARPS ? sml[lane] : make_float2(-CUDART_INF_F, 0.f);
+          M = warp_max(mlj.x);
+          const float wj = (M > -CUDART_INF_F && lane < WARPS) ? fast_exp2((mlj.x - M) * kLog2e) : 0.f;
+          Lsum = warp_sum(mlj.y * wj);
 #pragma unroll
-        for (int e = 0; e < PER; ++e) o[e] = 0.f;
+          for (int e = 0; e < PER; ++e) o[e] = 0.f;
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) {
-          const float ww = __shfl_sync(0xffffffffu, wj, w);
-          if (ww > 0.f) {                                      // warps without a tile in the segment wrote no partial
-            const PV_t v = *reinterpret_cast<const PV_t*>(sb + w * D + lane * PER);
-            const float* vf = reinterpret_cast<const float*>(&v);
+          for (int w = 0; w < WARPS; ++w) {
+            const float ww = __shfl_sync(0xffffffffu, wj, w);
+            if (ww > 0.f) {                                      // warps without a tile in the segment wrote no partial
+              const PV_t v = *reinterpret_cast<const PV_t*>(sb + w * D + lane * PER);
+              const float* vf = reinterpret_cast<const float*>(&v);
 #pragma unroll
-            for (int e = 0; e < PER; ++e) o[e] = fmaf(vf[e], ww, o[e]);
+              for (int e = 0; e < PER; ++e) o[e] = fmaf(vf[e], ww, o[e]);
+            }
           }
         }
-      }
-      __syncwarp();
-      if (lane == 0) {
-        sctl[0] = 0;
-        __threadfence_block();
-        sctl[1] = use + 1;                                     // hand the buffer to segment seg_seq + step_seg_bufs(WARPS)
-      }
+        __syncwarp();
+        if (lane == 0) {
+          ctl[0] = 0;
+          __threadfence_block();
+          ctl[1] = use + 1;                                      // hand the buffer to segment seq + NB
+        }
 
-      // ---- global level: the CTAs whose ranges intersect row i --------------------------------------------------------
-      const unsigned tf = static_cast<unsigned>(i) * p.tpr;
-      const int o_first = static_cast<int>(((tf + 1) * R.geff - 1) / R.T);
-      const int o_last = static_cast<int>(((tf + p.tpr) * R.geff - 1) / R.T);
-      const int n_grp = o_last - o_first + 1;
-      if (n_grp == 1) {
-        emit_row(l, row, o, Lsum > 0.f ? 1.f / Lsum : 0.f, M);
-        continue;
-      }
-      {
-        const int64_t slot = static_cast<int64_t>(l) * p.slots + R.vcta + i;
-        *reinterpret_cast<PV_t*>(p.part + slot * D + lane * PER) = *reinterpret_cast<const PV_t*>(o);
-        if (lane == 0) p.part_ml[slot] = make_float2(M, Lsum);
-      }
-      __syncwarp();
-      unsigned prev = 0;
-      unsigned int* ticket = p.tickets + static_cast<int64_t>(l) * p.rows + row;
-      if (lane == 0) {
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");     // release: the partial is visible device-wide
-        prev = atomicAdd(ticket, 1u);
-      }
-      prev = __shfl_sync(0xffffffffu, prev, 0);
-      STAMP(l, 5);                                         // CTA partial published, ticket taken
-      if (prev != static_cast<unsigned>(n_grp - 1)) continue;
-      asm volatile("fence.acq_rel.gpu;" ::: "memory");       // acquire side
+        // global level: the CTAs whose ranges intersect row i
+        const unsigned tf = static_cast<unsigned>(i) * p.tpr;
+        const int o_first = static_cast<int>(((tf + 1) * R.geff - 1) / R.T);
+        const int o_last = static_cast<int>(((tf + p.tpr) * R.geff - 1) / R.T);
+        const int n_grp = o_last - o_first + 1;
+        if (n_grp == 1) {
+          emit_row(l, row, o, Lsum > 0.f ? 1.f / Lsum : 0.f, M);
+          STAMP(l, 7);
+          continue;
+        }
+        {
+          const int64_t slot = static_cast<int64_t>(l) * p.slots + R.vcta + i;
+          *reinterpret_cast<PV_t*>(p.part + slot * D + lane * PER) = *reinterpret_cast<const PV_t*>(o);
+          if (lane == 0) p.part_ml[slot] = make_float2(M, Lsum);
+        }
+        __syncwarp();
+        unsigned prev = 0;
+        unsigned int* ticket = p.tickets + static_cast<int64_t>(l) * p.rows + row;
+        if (lane == 0) {
+          asm volatile("fence.acq_rel.gpu;" ::: "memory");     // release: the partial is visible device-wide
+          prev = atomicAdd(ticket, 1u);
+        }
+        prev = __shfl_sync(0xffffffffu, prev, 0);
+        STAMP(l, 5);
+        if (prev != static_cast<unsigned>(n_grp - 1)) continue;
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");       // acquire side
 
-      // last CTA of the row: merge its n_grp partials (a handful: rows / CTAs)
-      {
+        // last CTA of the row: merge its n_grp partials (a handful: rows / CTAs)
         const int64_t base = static_cast<int64_t>(l) * p.slots + o_first + i;
         const float* rec = p.part + base * D + lane * PER;
         const float2* ml = p.part_ml + base;
@@ -742,7 +436,7 @@ __global__ void __launch_bounds__((WARPS + (COMM ? 1 : 0)) * 32, 1) decode_step_
         float og[PER];
 #pragma unroll
         for (int e = 0; e < PER; ++e) og[e] = 0.f;
-        constexpr int kU = 8;                              // partial loads in flight per lane
+        constexpr int kU = 8;                                  // partial loads in flight per lane
 #pragma unroll 1
         for (int c0 = 0; c0 < n_grp; c0 += kU) {
           const int nc = min(kU, n_grp - c0);
@@ -768,23 +462,319 @@ __global__ void __launch_bounds__((WARPS + (COMM ? 1 : 0)) * 32, 1) decode_step_
           }
         }
         const float Lg = warp_sum(Lp);
-        if (lane == 0) *ticket = 0;                        // self-cleaning ticket for the next step
-        STAMP(l, 6);                                       // row merged
+        if (lane == 0) *ticket = 0;                            // self-cleaning ticket for the next step
+        STAMP(l, 6);
         emit_row(l, row, og, Lg > 0.f ? 1.f / Lg : 0.f, Mg);
-        STAMP(l, 7);                                       // row stored and signalled
+        STAMP(l, 7);
+      }
+    }
+    // head sharding: the launch completes only when every rank's rows of every layer are in the local gather buffer
+    // (chained steps have already waited for all layers but the last)
+    if (p.final_wait && blockIdx.x == 0) {
+#pragma unroll 1
+      for (int l = p.chain ? p.L - 1 : 0; l < p.L; ++l) wait_layer(l);
+    }
+  } else {
+    // ================= COMPUTE warps: stream K/V tiles, nothing else =====================================================
+    const uint64_t pol = policy_evict_first();
+    // issue side: this warp's tile sequence, STAGES tiles ahead of the consumer, walking on across layers.  This warp's
+    // tiles of layer l are the range positions (warp + l) % WARPS, + WARPS, ... (the offset rotates with the layer so that
+    // the warps taking one tile more than the others change from layer to layer).
+    int il = 0, ik = 0, ike = 0, ii = 0, ij = 0;
+    bool irow_new = true;
+    int inlh = p.H;
+    unsigned long long ihm = ~0ull;
+    const __half* ikp = nullptr;
+    const __half* ivp = nullptr;
+    auto issue_enter = [&](int l) {
+      const RangeRec r = layer_range(l);
+      ik = r.cs + (warp + l) % WARPS; ike = r.ce; inlh = r.nlh; ihm = r.hm;
+      if (ik < ike) { ii = ik / p.tpr; ij = ik - ii * p.tpr; irow_new = true; }
+    };
+    auto issue_seek = [&]() {
+      while (il < p.L && ik >= ike) {
+        ++il;
+        if (il < p.L) issue_enter(il);
+      }
+    };
+    issue_enter(0);
+    issue_seek();
+    auto issue_next = [&](int s) {                 // copy the issue cursor's tile into stage s, move the cursor on
+      if (il >= p.L) return;
+      if (irow_new) {
+        int bi, h;
+        row_coords(ii, inlh, ihm, bi, h);
+        const SpattenStepLayer* ly = lys + il;
+        const int64_t off = bi * p.stride_b + (h / p.n_rep) * p.stride_h;
+        ikp = static_cast<const __half*>(ly->k_cache) + off;
+        ivp = static_cast<const __half*>(ly->v_cache) + off;
+        irow_new = false;
+      }
+      const int ncopy = min(kTile, p.kv_len - ij * kTile);
+      if (ncopy > 0)
+        issue_kv_copies(lane == 0, wsm_u32 + s * kStageBytes, wsm_u32 + s * kStageBytes + kTileBytes,
+                        ikp + static_cast<int64_t>(ij) * (kTile * D), ivp + static_cast<int64_t>(ij) * (kTile * D),
+                        static_cast<uint32_t>(ncopy) * kRowBytes, bars_u32 + s * 8, pol);
+      ik += WARPS; ij += WARPS;
+      while (ij >= p.tpr) { ij -= p.tpr; ++ii; irow_new = true; }
+      if (ik >= ike) issue_seek();
+    };
+    // RoPE rows of one tile: cos | sin for the passes of this lane's key group (L2 resident table)
+    auto load_table = [&](int tok0, HV (&cs)[PASSES], HV (&sn)[PASSES]) {
+      if (tok0 + kTile <= p.rope_len) {
+        const __half* r = p.rope + static_cast<int64_t>(tok0 + g) * D + c * E2;
+#pragma unroll
+        for (int ps = 0; ps < PASSES; ++ps) {
+          *reinterpret_cast<Vec*>(&cs[ps]) = __ldg(reinterpret_cast<const Vec*>(r + ps * 4 * D));
+          *reinterpret_cast<Vec*>(&sn[ps]) = __ldg(reinterpret_cast<const Vec*>(r + ps * 4 * D + D / 2));
+        }
+      } else {
+#pragma unroll
+        for (int ps = 0; ps < PASSES; ++ps) {
+          const int j = min(tok0 + ps * 4 + g, p.rope_len - 1);
+          const __half* r = p.rope + static_cast<int64_t>(j) * D + c * E2;
+          *reinterpret_cast<Vec*>(&cs[ps]) = __ldg(reinterpret_cast<const Vec*>(r));
+          *reinterpret_cast<Vec*>(&sn[ps]) = __ldg(reinterpret_cast<const Vec*>(r + D / 2));
+        }
+      }
+    };
+
+#pragma unroll 1
+    for (int s = 0; s < STAGES; ++s) issue_next(s);
+
+    unsigned phase = 0;     // bit s = parity the next wait on stage s uses
+    int s = 0;
+    unsigned seg_seq = 0;   // segments (CTA range x row) this CTA has walked past: selects the shared-memory buffer
+    HV cs[PASSES], sn[PASSES];
+    int table_for = -1;     // token offset the RoPE registers currently hold (-1: none)
+
+#pragma unroll 1
+    for (int l = 0; l < p.L; ++l) {
+      const RangeRec R = layer_range(l);
+      const SpattenStepLayer* ly = lys + l;
+      if (R.cs >= R.ce) continue;
+      const int i0 = R.cs / p.tpr, i1 = (R.ce - 1) / p.tpr;
+      int k = R.cs + (warp + l) % WARPS;                     // this warp's next tile in the layer's list
+
+#pragma unroll 1
+      for (int i = i0; i <= i1; ++i, ++seg_seq) {
+        // ---- one segment: the part of row i inside this CTA's range; this warp's tiles of it --------------------------
+        const int row_end = min(R.ce, (i + 1) * p.tpr);
+        const bool have = k < row_end;
+        volatile unsigned* ctl = seg_ctl[seg_seq % NB];
+        const unsigned use = seg_seq / NB;
+        float fin[PER];
+        float m = -CUDART_INF_F, lsum = 0.f;
+        if (have) {
+          int j = k - i * p.tpr;
+          if (table_for != j * kTile) load_table(j * kTile, cs, sn);
+          int bi, h;
+          row_coords(i, R.nlh, R.hm, bi, h);
+          const int row = bi * p.H + h;
+          const int kvh = h / p.n_rep;
+          bool writer = (h % p.n_rep) == 0;
+          if (p.head_mask) {
+            const unsigned long long grp = (R.hm >> (kvh * p.n_rep)) & (p.n_rep >= 64 ? ~0ull : ((1ull << p.n_rep) - 1ull));
+            writer = h == kvh * p.n_rep + (__ffsll(static_cast<long long>(grp)) - 1);   // first live head of the kv group
+          }
+          __half* lg = ly->logits ? static_cast<__half*>(ly->logits) + static_cast<int64_t>(row) * p.logits_stride : nullptr;
+          STAMP(l, 0);
+          // the rotated query of this segment, published by the query warp (which has also passed the chain wait)
+          while (ctl[2] != use + 1) __nanosleep(20);
+          __threadfence_block();
+          HV qlr, qhr;
+          {
+            const __half* qs = seg_q(seg_seq);
+            *reinterpret_cast<Vec*>(&qlr) = *reinterpret_cast<const Vec*>(qs + c * E2);
+            *reinterpret_cast<Vec*>(&qhr) = *reinterpret_cast<const Vec*>(qs + D / 2 + c * E2);
+          }
+          float accl[E2], acch[E2];
+#pragma unroll
+          for (int e = 0; e < E2; ++e) accl[e] = acch[e] = 0.f;
+
+#pragma unroll 1
+          for (; k < row_end; k += WARPS, j += WARPS) {
+            // ---- one tile -------------------------------------------------------------------------------------------
+            const int tok0 = j * kTile;
+            const int ntok = min(kTile, p.n_total - tok0);           // valid tokens (incl. the appended one)
+            const int ncopy = max(0, min(kTile, p.kv_len - tok0));   // of which bulk-copied from the cache
+            uint8_t* Ks = wsm + s * kStageBytes;
+            uint8_t* Vs = Ks + kTileBytes;
+
+            const bool generic_writes = ntok < kTile;                // only the last tile of a row
+            if (generic_writes) {
+              // zero the rows the copy does not write, so masked lanes multiply finite numbers
+#pragma unroll 1
+              for (int o = ncopy * kRowBytes + lane * 16; o < kTileBytes; o += 32 * 16) {
+                *reinterpret_cast<uint4*>(Ks + o) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(Vs + o) = make_uint4(0, 0, 0, 0);
+              }
+              __syncwarp();
+            }
+            if (ncopy > 0) {
+              if (!mbar_try_wait(&bars[s], (phase >> s) & 1u)) {
+                const long long tw = clock64();
+                while (!mbar_try_wait(&bars[s], (phase >> s) & 1u)) {
+                  if (clock64() - tw > 4000000000ll) __trap();    // a lost copy must fail the launch, not wedge the GPU
+                }
+              }
+              phase ^= 1u << s;
+            }
+            if (DBG && k == R.cs + (warp + l) % WARPS) STAMP(l, 2);
+            if (ncopy < ntok) {
+              // the appended token (modify_llama.py:95-100): its un-rotated K/V row goes into the tile and into slot kv_len
+              constexpr int kChunks = kRowBytes / 16;
+              const int r = p.kv_len - tok0;
+              const int which = lane / kChunks, ch = lane % kChunks;
+#pragma unroll 1
+              for (int w = which; w < 2; w += 32 / kChunks) {
+                const __half* src = static_cast<const __half*>(w ? ly->v_new : ly->k_new) +
+                                    (static_cast<int64_t>(bi) * p.H_kv + kvh) * D + ch * 8;
+                const uint4 val = *reinterpret_cast<const uint4*>(src);
+                *reinterpret_cast<uint4*>((w ? Vs : Ks) + r * kRowBytes + ch * 16) = val;
+                if (writer) {
+                  __half* dst = static_cast<__half*>(w ? ly->v_cache : ly->k_cache) + bi * p.stride_b + kvh * p.stride_h +
+                                static_cast<int64_t>(p.kv_len) * D + ch * 8;
+                  *reinterpret_cast<uint4*>(dst) = val;
+                }
+              }
+              __syncwarp();
+            }
+
+            // scores of the tile: rotated key rounded to fp16 after every elementwise op (:27), products summed in fp32
+            float d[PASSES];
+#pragma unroll
+            for (int ps = 0; ps < PASSES; ++ps) {
+              const int tl = ps * 4 + g;
+              HV kl, kh;
+              *reinterpret_cast<Vec*>(&kl) = *reinterpret_cast<const Vec*>(Ks + tl * kRowBytes + c * VB);
+              *reinterpret_cast<Vec*>(&kh) = *reinterpret_cast<const Vec*>(Ks + tl * kRowBytes + D + c * VB);
+              float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+              for (int e = 0; e < NH2; ++e) {
+                const __half2 rl = __hsub2_rn(__hmul2_rn(kl.h[e], cs[ps].h[e]), __hmul2_rn(kh.h[e], sn[ps].h[e]));
+                const __half2 rh = __hadd2_rn(__hmul2_rn(kh.h[e], cs[ps].h[e]), __hmul2_rn(kl.h[e], sn[ps].h[e]));
+                d0 = fhfma_lo(rl, qlr.h[e], d0);             // fp16 x fp16 products are exact in fp32 (FHFMA): same sums
+                d0 = fhfma_hi(rl, qlr.h[e], d0);             // as fmaf(float(q), float(k), d) without the conversions
+                d1 = fhfma_lo(rh, qhr.h[e], d1);
+                d1 = fhfma_hi(rh, qhr.h[e], d1);
+              }
+              d[ps] = d0 + d1;
+            }
+            // the RoPE registers are free: fetch the rows of this warp's NEXT tile (same segment, next row of the layer, or
+            // the next layer's first tile) under the rest of this one
+            {
+              int nj = -1;
+              if (k + WARPS < R.ce) {
+                nj = j + WARPS;
+                while (nj >= p.tpr) nj -= p.tpr;
+              } else if (l + 1 < p.L) {
+                const RangeRec Rn = layer_range(l + 1);
+                const int kn = Rn.cs + (warp + l + 1) % WARPS;
+                if (kn < Rn.ce) nj = kn % p.tpr;
+              }
+              table_for = -1;
+              if (nj >= 0) { load_table(nj * kTile, cs, sn); table_for = nj * kTile; }
+            }
+
+#pragma unroll
+            for (int o = 1; o <= 4; o <<= 1) {
+#pragma unroll
+              for (int ps = 0; ps < PASSES; ++ps) d[ps] += __shfl_xor_sync(0xffffffffu, d[ps], o);
+            }
+            // fp16 logit exactly as the reference forms it: fp16(matmul) / sqrt(D) -> fp16 (:111-113)
+            float sc[PASSES];
+            float mx = -CUDART_INF_F;
+#pragma unroll
+            for (int ps = 0; ps < PASSES; ++ps) {
+              const int tl = ps * 4 + g;
+              const bool valid = tl < ntok;
+              const __half s16 = __float2half_rn(div_by_const(__half2float(__float2half_rn(d[ps])), p.sqrt_d, p.rsqrt_d));
+              if (valid && c == 0 && lg) lg[tok0 + tl] = s16;
+              sc[ps] = valid ? __half2float(s16) : -CUDART_INF_F;
+              mx = fmaxf(mx, sc[ps]);
+            }
+            // online softmax (:135): m is warp-uniform; l and acc are per key group until the segment ends
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+            const float m_new = fmaxf(m, mx);
+            if (m_new > -CUDART_INF_F) {
+              if (m_new != m) {
+                const float corr = fast_exp2((m - m_new) * kLog2e);
+                lsum *= corr;
+#pragma unroll
+                for (int e = 0; e < E2; ++e) { accl[e] *= corr; acch[e] *= corr; }
+                m = m_new;
+              }
+              // the probabilities enter P.V as fp16, as in the reference (softmax(...).to(fp16) @ V, :135-138); the running
+              // sum uses the same rounded values, so the final normalisation is exact for what was accumulated
+              __half2 ph[PASSES];
+#pragma unroll
+              for (int ps = 0; ps < PASSES; ++ps) {
+                ph[ps] = __float2half2_rn(fast_exp2((sc[ps] - m) * kLog2e));
+                lsum += __low2float(ph[ps]);
+              }
+              // P.V (:138)
+#pragma unroll
+              for (int ps = 0; ps < PASSES; ++ps) {
+                const int tl = ps * 4 + g;
+                HV vl, vh;
+                *reinterpret_cast<Vec*>(&vl) = *reinterpret_cast<const Vec*>(Vs + tl * kRowBytes + c * VB);
+                *reinterpret_cast<Vec*>(&vh) = *reinterpret_cast<const Vec*>(Vs + tl * kRowBytes + D + c * VB);
+#pragma unroll
+                for (int e = 0; e < NH2; ++e) {
+                  accl[2 * e] = fhfma_lo(vl.h[e], ph[ps], accl[2 * e]);
+                  accl[2 * e + 1] = fhfma_hi(vl.h[e], ph[ps], accl[2 * e + 1]);
+                  acch[2 * e] = fhfma_lo(vh.h[e], ph[ps], acch[2 * e]);
+                  acch[2 * e + 1] = fhfma_hi(vh.h[e], ph[ps], acch[2 * e + 1]);
+                }
+              }
+            }
+
+            // stage s is free: refill it with this warp's tile STAGES ahead (possibly the next layer's)
+            if (generic_writes) fence_proxy_async();         // generic-proxy writes above vs the async-proxy copy below
+            __syncwarp();
+            issue_next(s);
+            s = (s + 1 == STAGES) ? 0 : s + 1;
+          }
+          STAMP(l, 3);
+
+          // ---- this warp's tiles of the segment are done: reduce-scatter over the 4 key groups (lane bits 3 and 4) -----
+          lsum += __shfl_xor_sync(0xffffffffu, lsum, 8);
+          lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
+          float keep[E2];
+          const bool up = (g & 1) != 0;                 // bit 3: keep the upper half-row, send the lower
+#pragma unroll
+          for (int e = 0; e < E2; ++e) {
+            const float send = up ? accl[e] : acch[e];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+            keep[e] = (up ? acch[e] : accl[e]) + recv;
+          }
+          const bool up2 = (g & 2) != 0;                // bit 4: keep the upper PER of the E2 values
+#pragma unroll
+          for (int e = 0; e < PER; ++e) {
+            const float send = up2 ? keep[e] : keep[e + PER];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+            fin[e] = (up2 ? keep[e + PER] : keep[e]) + recv;
+          }
+          const int d0 = (g & 1) * (D / 2) + c * E2 + (g >> 1) * PER;   // first of the PER dims this lane owns
+          *reinterpret_cast<PV_t*>(seg_part(seg_seq) + warp * D + d0) = *reinterpret_cast<const PV_t*>(fin);
+        } else {
+          // no tile of this segment: the buffer must still be ours before (m, l) goes in
+          while (ctl[1] != use) __nanosleep(40);
+        }
+        // ---- check in at the segment's buffer; the merge warp does the rest ---------------------------------------------
+        if (lane == 0) seg_ml(seg_seq)[warp] = make_float2(m, lsum);
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence_block();
+          atomicAdd(const_cast<unsigned*>(&ctl[0]), 1u);
+        }
       }
     }
   }
 
   // ---- step epilogue ------------------------------------------------------------------------------------------------
-  // head sharding: the launch completes only when every rank's rows of every layer are in the local gather buffer
-  // (chained steps have already waited for all layers but the last)
-  if (p.final_wait && blockIdx.x == 0 && warp == 0) {
-#pragma unroll 1
-    for (int l = p.chain ? p.L - 1 : 0; l < p.L; ++l) wait_layer(l);
-  }
-  if (COMM && lane == 0) atomicAdd(&mail_ctl[1], 1u);      // this compute warp will hand over no more rows
-  }   // compute warps
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -801,41 +791,31 @@ __global__ void __launch_bounds__((WARPS + (COMM ? 1 : 0)) * 32, 1) decode_step_
 template <int D, int WARPS, int STAGES, int PASSES>
 constexpr size_t step_smem_bytes() {
   return static_cast<size_t>(WARPS) * STAGES * 2 * (4 * PASSES) * D * 2 + WARPS * STAGES * 8 +
-         static_cast<size_t>(step_seg_bufs(WARPS)) * (WARPS * D + WARPS * 2 + 4) * sizeof(float) +
-         kStepSmemLayers * sizeof(SpattenStepLayer);
+         static_cast<size_t>(step_seg_bufs(WARPS)) * (WARPS * D + WARPS * 2 + D / 2) * sizeof(float) +
+         kStepSmemLayers * (sizeof(SpattenStepLayer) + sizeof(RangeRec));
 }
 
-// Kernel variants: (warps per CTA, ring stages per warp).  192 KiB of K/V ring per SM either way.
-//   0: 8 warps x 3 stages x 16-token tiles     1: 16 warps x 3 stages x 8-token tiles (4 warps per scheduler, <= 128 regs)
-//   2: 12 warps x 2 stages x 16-token tiles   3: 12 warps x 4 stages x 8-token tiles
-//   4: 8 x 2 x 16 tok   5: 8 x 2 x 8 tok   6: 16 x 2 x 8 tok   7: 8 x 4 x 8 tok  (shallower rings: less queueing in front of
-//   the latency-critical query / flag loads)
-constexpr int kStepVariants = 10;
-constexpr int kStepMaxWarps = 16;
+// Kernel variants: (compute warps per CTA, ring stages per warp); every build adds the query warp and the merge warp.
+// 192 KiB (or 128 KiB) of K/V ring per SM.
+//   0: 8 warps x 3 stages   1: 12 warps x 2 stages   2: 8 warps x 2 stages   3: variant 1 with %globaltimer stamps
+constexpr int kStepVariants = 4;
+constexpr int kStepMaxWarps = 12;
 using StepKernel = void (*)(const StepParams);
 struct StepVariant {
   StepKernel kernel;
   int warps, tile;
   size_t smem;
-  int comm = 0;            // 1: one extra warp per CTA that does the NVLink stores and system-scope releases
 };
 template <int D>
 static StepVariant step_variant(int v) {
-  if (v == 1) return {decode_step_kernel<D, 16, 3, 2>, 16, 8, step_smem_bytes<D, 16, 3, 2>()};
-  if (v == 2) return {decode_step_kernel<D, 12, 2, 4>, 12, 16, step_smem_bytes<D, 12, 2, 4>()};
-  if (v == 3) return {decode_step_kernel<D, 12, 4, 2>, 12, 8, step_smem_bytes<D, 12, 4, 2>()};
-  if (v == 4) return {decode_step_kernel<D, 8, 2, 4>, 8, 16, step_smem_bytes<D, 8, 2, 4>()};
-  if (v == 5) return {decode_step_kernel<D, 8, 2, 2>, 8, 8, step_smem_bytes<D, 8, 2, 2>()};
-  if (v == 6) return {decode_step_kernel<D, 16, 2, 2>, 16, 8, step_smem_bytes<D, 16, 2, 2>()};
-  if (v == 7) return {decode_step_kernel<D, 8, 4, 2>, 8, 8, step_smem_bytes<D, 8, 4, 2>()};
-  if (v == 8) return {decode_step_kernel<D, 8, 3, 4, true>, 8, 16, step_smem_bytes<D, 8, 3, 4>()};   // timeline build
-  if (v == 9) return {decode_step_kernel<D, 8, 2, 4, false, true>, 8, 16, step_smem_bytes<D, 8, 2, 4>(), 1};   // + communication warp
+  if (v == 1) return {decode_step_kernel<D, 12, 2, 4>, 12, 16, step_smem_bytes<D, 12, 2, 4>()};
+  if (v == 2) return {decode_step_kernel<D, 8, 2, 4>, 8, 16, step_smem_bytes<D, 8, 2, 4>()};
+  if (v == 3) return {decode_step_kernel<D, 12, 2, 4, true>, 12, 16, step_smem_bytes<D, 12, 2, 4>()};   // timeline build
   return {decode_step_kernel<D, 8, 3, 4>, 8, 16, step_smem_bytes<D, 8, 3, 4>()};
 }
 // Measured on B200 (profiles/r2_step_variants.jsonl): with few tiles per warp and layer (BASELINE config 2: 27.7
-// tiles per SM) twelve warps hide the segment-boundary latencies better (8.6 vs 9.2 us per layer); long rows stream
-// best from eight warps with two-stage rings (0.97 of the measured HBM peak at b=8, H=5, n=16384).
-// SPATTEN_STEP_VARIANT=<n> overrides the choice (tools/microbench.py).
+// tiles per SM) twelve compute warps hide the segment-boundary latencies better; long rows stream best from eight warps
+// with two-stage rings.  SPATTEN_STEP_VARIANT=<n> overrides the choice (tools/microbench.py).
 static int step_variant_choice(long tiles_per_layer, int sms) {
   static int forced = -2;
   if (forced == -2) {
@@ -844,11 +824,8 @@ static int step_variant_choice(long tiles_per_layer, int sms) {
     if (forced < 0 || forced >= kStepVariants) forced = -1;
   }
   if (forced >= 0) return forced;
-  return tiles_per_layer >= 64L * sms ? 4 : 2;
+  return tiles_per_layer >= 64L * sms ? 2 : 1;
 }
-
-// the same choice among the builds that carry a communication warp
-static int step_comm_variant(long, int) { return 9; }   // 8 warps x 2 stages + communication warp (a 12-warp build does not fit)
 
 template <int D>
 static int step_grid(int variant, int& grid) {
@@ -860,7 +837,7 @@ static int step_grid(int variant, int& grid) {
   cudaError_t e = cudaFuncSetAttribute(sv.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sv.smem));
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(decode_step_kernel)");
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sv.kernel, (sv.warps + sv.comm) * 32, sv.smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sv.kernel, (sv.warps + 2) * 32, sv.smem);
   if (e != cudaSuccess || per_sm < 1) return cuda_fail(e, "decode_step_kernel does not fit on an SM");
   const int sms = sm_count();
   if (sms <= 0) return SPATTEN_ERR_CUDA;
@@ -939,8 +916,7 @@ extern "C" int spatten_decode_step(const SpattenStepArgs* a, void* stream) {
   const long tiles16 = static_cast<long>(a->batch) * a->num_heads * ((n_total + 15) / 16);
   const int sms_now = sm_count();
   if (sms_now <= 0) return SPATTEN_ERR_CUDA;
-  // head sharding over NVLink: the build with a communication warp (unless a variant is forced for measurements)
-  const int variant = g_step_dbg ? 8 : (((a->n_peers > 1 || (a->flags & SPATTEN_STEP_SHARDED_LAYOUT)) && !getenv("SPATTEN_STEP_VARIANT")) ? step_comm_variant(tiles16, sms_now) : step_variant_choice(tiles16, sms_now));
+  const int variant = g_step_dbg ? 3 : step_variant_choice(tiles16, sms_now);
   if (int rc = (a->head_dim == 128 ? step_grid<128>(variant, grid) : step_grid<64>(variant, grid))) return rc;
   const StepVariant sv = a->head_dim == 128 ? step_variant<128>(variant) : step_variant<64>(variant);
 
@@ -1012,7 +988,7 @@ extern "C" int spatten_decode_step(const SpattenStepArgs* a, void* stream) {
 
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3((sv.warps + sv.comm) * 32);
+  cfg.blockDim = dim3((sv.warps + 2) * 32);
   cfg.dynamicSmemBytes = sv.smem;
   cfg.stream = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaLaunchKernelEx(&cfg, sv.kernel, p);

@@ -93,7 +93,7 @@ def step_timeline(b, H, D, n, L, chain=True):
     for _ in range(3):
         step.launch()
     torch.cuda.synchronize()
-    G, Wp = torch.cuda.get_device_properties(0).multi_processor_count, 8
+    G, Wp = torch.cuda.get_device_properties(0).multi_processor_count, 14      # 12 compute warps + query warp + merge warp
     buf = torch.zeros(L * G * Wp * 8, dtype=torch.int64, device=dev)
     lib.spatten_debug_set_step_timeline(C.c_void_p(buf.data_ptr()))
     step.launch()
