@@ -210,6 +210,9 @@ typedef struct SpattenStepArgs {
    * (SPATTEN_STEP_CHAIN) and, for the last layer, before it exits -- when the launch completes, every rank's rows
    * of every layer are in the local gather buffer. */
   int32_t n_peers;
+  int32_t self_peer;                    /* index of THIS rank in peer_out / peer_flags: rows are stored there first, and the
+                                           warp that finishes a layer copies the layer's slot to the other peers in one go
+                                           (one system-scope release per layer instead of NVLink stores per row) */
   void* peer_out[8];
   int64_t peer_layer_stride;
   void* peer_flags[8];

@@ -67,7 +67,7 @@ class StepArgs(C.Structure):
         ("cache_stride_b", C.c_int64), ("cache_stride_h", C.c_int64),
         ("logits_stride", C.c_int64), ("importance_stride", C.c_int64),
         ("rope", C.c_void_p), ("q_pos", C.c_void_p), ("head_mask", C.c_void_p), ("head_importance", C.c_void_p),
-        ("n_peers", C.c_int32), ("peer_out", C.c_void_p * 8), ("peer_layer_stride", C.c_int64),
+        ("n_peers", C.c_int32), ("self_peer", C.c_int32), ("peer_out", C.c_void_p * 8), ("peer_layer_stride", C.c_int64),
         ("peer_flags", C.c_void_p * 8), ("peer_flag_layer_stride", C.c_int64), ("wait_flags", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]

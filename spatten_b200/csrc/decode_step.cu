@@ -66,6 +66,8 @@ struct StepParams {
   int final_wait;          // wait for the last layer's flags before the kernel exits
   int sys_scope;           // flags live in peer memory
   float sqrt_d, rsqrt_d;
+  int self_peer;           // index of this rank in peer_out
+  unsigned int* layer_rows; // [L] rows of a layer stored so far on this GPU (head sharding: one system-scope release per layer)
   unsigned long long* dbg; // optional [L][grid][warps][8] globaltimer stamps (tools/microbench.py --step-timeline)
 };
 
@@ -280,10 +282,18 @@ __global__ void __launch_bounds__((WARPS + 2) * 32, 1) decode_step_kernel(const 
     auto signal_row = [&](int layer) {
       if (p.n_flag == 0) return;
       __syncwarp();
-      if (lane < p.n_flag) {
+      if (p.sys_scope) {
+        // Head sharding: the row went into this rank's slot of the LOCAL gather buffer; count it (GPU scope).  The layer is
+        // shipped to the peers by the merge warp of a designated CTA once the count is complete (ship_layer below): a
+        // system-scope release per row costs 2.5 us per layer even on this warp, and giving the extra work to whichever
+        // warp stores the last row makes the slowest CTA slower still (measured: 9.0 -> 13.0 us per layer).
+        if (lane == 0) {
+          asm volatile("fence.acq_rel.gpu;" ::: "memory");
+          atomicAdd(p.layer_rows + layer, 1u);
+        }
+      } else if (lane < p.n_flag) {
         unsigned int* f = p.flag_ptr[lane] + static_cast<int64_t>(layer) * p.flag_layer_stride;
-        if (p.sys_scope) asm volatile("fence.acq_rel.sys;\n\tred.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(f) : "memory");
-        else asm volatile("fence.acq_rel.gpu;\n\tred.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(f) : "memory");
+        asm volatile("fence.acq_rel.gpu;\n\tred.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(f) : "memory");
       }
     };
     // lane owns dims [lane*PER, lane*PER + PER) of the finished row: normalise, round, store (locally or to every peer)
@@ -301,12 +311,10 @@ __global__ void __launch_bounds__((WARPS + 2) * 32, 1) decode_step_kernel(const 
         if (PER == 4) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(oh16);
         else *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(oh16);
       } else {
-#pragma unroll 1
-        for (int r = 0; r < p.n_out; ++r) {
-          __half* dst = p.peer_out[r] + static_cast<int64_t>(layer) * p.peer_layer_stride + off;
-          if (PER == 4) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(oh16);
-          else *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(oh16);
-        }
+        // head sharding: into this rank's slot of the LOCAL gather buffer; the layer's last row ships the slot (signal_row)
+        __half* dst = p.peer_out[p.self_peer] + static_cast<int64_t>(layer) * p.peer_layer_stride + off;
+        if (PER == 4) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(oh16);
+        else *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(oh16);
       }
       if (p.head_importance) {
         habs = warp_sum(habs);
@@ -324,6 +332,41 @@ __global__ void __launch_bounds__((WARPS + 2) * 32, 1) decode_step_kernel(const 
         }
       }
       signal_row(layer);
+    };
+    // ---- shipping (head sharding): layer l is sent by the merge warp of CTA (41 l + 7) mod G, between its own segments ----
+    auto ship_owner = [&](int l) { return static_cast<int>((41u * static_cast<unsigned>(l) + 7u) % static_cast<unsigned>(G)); };
+    int ship_l = 0;
+    auto ship_seek = [&]() { while (ship_l < p.L && ship_owner(ship_l) != static_cast<int>(blockIdx.x)) ++ship_l; };
+    if (!p.sys_scope) ship_l = p.L;
+    ship_seek();
+    auto try_ship = [&](bool block) {
+      while (ship_l < p.L) {
+        unsigned have = 0;
+        if (lane == 0) have = ld_relaxed(p.layer_rows + ship_l, 0);
+        have = __shfl_sync(0xffffffffu, have, 0);
+        if (static_cast<int>(have - flag_target) < 0) {
+          if (!block) return;
+          __nanosleep(100);
+          continue;
+        }
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");     // acquire: every row of the layer is in the local slot
+        const uint4* src = reinterpret_cast<const uint4*>(p.peer_out[p.self_peer] + static_cast<int64_t>(ship_l) * p.peer_layer_stride);
+        const int n16 = static_cast<int>(p.rows) * D / 8;
+#pragma unroll 1
+        for (int r = 0; r < p.n_out; ++r) {
+          if (r == p.self_peer) continue;
+          uint4* dst = reinterpret_cast<uint4*>(p.peer_out[r] + static_cast<int64_t>(ship_l) * p.peer_layer_stride);
+#pragma unroll 4
+          for (int k = lane; k < n16; k += 32) dst[k] = __ldcg(src + k);
+        }
+        __syncwarp();
+        if (lane < p.n_flag) {
+          unsigned int* f = p.flag_ptr[lane] + static_cast<int64_t>(ship_l) * p.flag_layer_stride;
+          asm volatile("fence.acq_rel.sys;\n\tred.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(f), "r"(p.rows) : "memory");
+        }
+        ++ship_l;
+        ship_seek();
+      }
     };
     unsigned seq = 0;
 #pragma unroll 1
@@ -366,7 +409,10 @@ __global__ void __launch_bounds__((WARPS + 2) * 32, 1) decode_step_kernel(const 
       for (int i = i0; i <= i1; ++i, ++seq) {
         volatile unsigned* ctl = seg_ctl[seq % NB];
         const unsigned use = seq / NB;
-        while (ctl[0] != static_cast<unsigned>(WARPS)) __nanosleep(40);      // every compute warp has checked in
+        while (ctl[0] != static_cast<unsigned>(WARPS)) {                     // every compute warp has checked in
+          try_ship(false);
+          __nanosleep(40);
+        }
         __threadfence_block();
         STAMP(l, 4);
         const float* sb = seg_part(seq);
@@ -468,6 +514,7 @@ __global__ void __launch_bounds__((WARPS + 2) * 32, 1) decode_step_kernel(const 
         STAMP(l, 7);
       }
     }
+    try_ship(true);                                            // whatever this CTA still owes the peers
     // head sharding: the launch completes only when every rank's rows of every layer are in the local gather buffer
     // (chained steps have already waited for all layers but the last)
     if (p.final_wait && blockIdx.x == 0) {
@@ -970,6 +1017,10 @@ extern "C" int spatten_decode_step(const SpattenStepArgs* a, void* stream) {
       p.peer_out[r] = static_cast<__half*>(a->peer_out[r]);
       p.flag_ptr[r] = static_cast<unsigned int*>(a->peer_flags[r]);
     }
+    SPATTEN_CHECK_ARG(a->self_peer >= 0 && a->self_peer < a->n_peers, "spatten_decode_step: self_peer out of range");
+    SPATTEN_CHECK_ARG((reinterpret_cast<uintptr_t>(a->peer_out[a->self_peer]) & 15) == 0 && a->peer_layer_stride % 8 == 0,
+                      "spatten_decode_step: gather buffers must be 16-byte aligned");
+    p.self_peer = a->self_peer;
     p.n_out = p.n_flag = p.wait_n = a->n_peers;
     p.peer_layer_stride = a->peer_layer_stride;
     p.flag_layer_stride = a->peer_flag_layer_stride;
@@ -977,6 +1028,7 @@ extern "C" int spatten_decode_step(const SpattenStepArgs* a, void* stream) {
     p.chain = chain ? 1 : 0;
     p.final_wait = 1;
     p.sys_scope = 1;
+    p.layer_rows = reinterpret_cast<unsigned int*>(ws + w.chain);
   } else if (chain) {
     p.n_out = 0;
     p.n_flag = p.wait_n = 1;

@@ -157,7 +157,7 @@ class PeerStepExchange:
         self.gathered = self.buf[:out_bytes].view(torch.float16).view(L, n, b, hl, D)
         self.flags = self.buf[self.flag_off:self.flag_off + L * n * 4].view(torch.int32).view(L, n)
         r = shard.rank
-        a.n_peers = n
+        a.n_peers, a.self_peer = n, r
         for p in range(n):
             a.peer_out[p] = self.ptrs[p] + r * self.slot_elems * 2            # layer 0, slot `rank` in rank p's buffer
             a.peer_flags[p] = self.ptrs[p] + self.flag_off + r * 4            # flag [0, rank] in rank p's memory
