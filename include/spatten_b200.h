@@ -231,12 +231,21 @@ int spatten_decode_step_host(const SpattenStepArgs* args, const void* in_host, v
 
 /* ------------------------------------------------------------------------------------------------
  * Prefill attention (q_len > 1) on the tcgen05 tensor cores.  Same reference lines as spatten_decode_attn
- * (modify_llama.py:86-144) in the reference's own three steps, because the full pre-mask logit matrix is an
- * output (`self.attn_scores`, :116-119): S = rope(Q).rope(K)^T (UMMA, RoPE fused into the operand staging,
- * fp16 logit formed as :111-113), P = softmax(S + mask) in fp32 (:132-137), O = P.V (UMMA).
- * The new K/V rows must already be in the cache (rows [kv_len - q_len, kv_len) for a plain prefill).
- * head_dim == 128.  `probs` is scratch of the same shape and strides as `logits`.
+ * (modify_llama.py:86-144); the full pre-mask logit matrix is an output (`self.attn_scores`, :116-119).
+ * The new K/V rows must already be in the cache (rows [kv_len - q_len, kv_len) for a plain prefill).  head_dim == 128.
+ *
+ * Fused path (csrc/prefill_fused.cu), taken when `scratch_bytes` >= spatten_prefill_scratch_bytes(...): Q and K are
+ * rotated once and Q/K/V re-tiled into tensor-core operand images in `probs` (used as plain scratch); ONE
+ * warp-specialised kernel then computes S = rope(Q).rope(K)^T per 128x128 tile, writes the fp16 logits (:111-113) once,
+ * keeps the row max / row sum, recomputes S for the tiles the mask leaves alive, and accumulates O += P.V with the
+ * accumulator in tensor memory, plus the column sums of P (`importance`).  The additive mask is classified on the
+ * device: the standard causal mask (0 on and below the diagonal shifted by kv_len - q_len, <= -60000 above) becomes a
+ * predicate and fully masked tiles are skipped; any other mask is applied element by element (:127-132).
+ * Legacy path (csrc/prefill_umma.cu; `scratch_bytes` == 0 or SPATTEN_PREFILL_LEGACY): the reference's own three steps
+ * as three launches; `probs` must then be scratch of the same shape and strides as `logits`.
  * ---------------------------------------------------------------------------------------------- */
+#define SPATTEN_PREFILL_CAUSAL 1u   /* mask == NULL means "standard causal mask" instead of "no mask" */
+#define SPATTEN_PREFILL_LEGACY 2u   /* force the three-launch path */
 typedef struct SpattenPrefillArgs {
   uint32_t struct_size;
   int32_t batch, num_heads, num_kv_heads, head_dim, q_len, kv_len, rope_len;
@@ -249,13 +258,18 @@ typedef struct SpattenPrefillArgs {
   const void* mask;         /* optional fp16 additive [b, q_len, kv_len] */
   void* logits;             /* out fp16 attn_scores[b, h, q, :] */
   int64_t logits_stride_b, logits_stride_h, logits_stride_q;   /* elements */
-  void* probs;              /* scratch fp16, same strides */
+  void* probs;              /* scratch (16-byte aligned): operand images (fused) or fp16 probabilities with the logits' strides (legacy) */
   void* out;                /* fp16 [b, q_len, H, D] */
   float* importance;        /* optional fp32 [b, H, importance_stride]: += sum over the q_len query rows of the softmax
                                probabilities (column sums of P: the cumulative token importance of README.md:21, SURVEY.md
-                               8f rank 2); one extra pass over `probs` */
+                               8f rank 2) */
   int64_t importance_stride;/* elements between heads (>= kv_len) */
+  uint32_t flags;           /* SPATTEN_PREFILL_* */
+  uint32_t reserved0;
+  int64_t scratch_bytes;    /* size of `probs` in bytes; 0 = legacy contract (same shape as logits) */
 } SpattenPrefillArgs;
+/* bytes of scratch the fused path needs for these shapes */
+int64_t spatten_prefill_scratch_bytes(int32_t batch, int32_t num_heads, int32_t num_kv_heads, int32_t q_len, int32_t kv_len);
 int spatten_prefill_attn(const SpattenPrefillArgs* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

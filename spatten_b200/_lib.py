@@ -84,7 +84,12 @@ class PrefillArgs(C.Structure):
         ("logits", C.c_void_p), ("logits_stride_b", C.c_int64), ("logits_stride_h", C.c_int64),
         ("logits_stride_q", C.c_int64), ("probs", C.c_void_p), ("out", C.c_void_p),
         ("importance", C.c_void_p), ("importance_stride", C.c_int64),
+        ("flags", C.c_uint32), ("reserved0", C.c_uint32), ("scratch_bytes", C.c_int64),
     ]
+
+
+PREFILL_CAUSAL = 1
+PREFILL_LEGACY = 2
 
 
 class SelectArgs(C.Structure):
@@ -209,6 +214,8 @@ def _bind_optional(lib):
     lib.spatten_sparse_pv.argtypes = [C.POINTER(SparsePvArgs), C.c_void_p]
     lib.spatten_local_v_attn.argtypes = [C.POINTER(LocalVArgs), C.c_void_p]
     lib.spatten_prefill_attn.argtypes = [C.POINTER(PrefillArgs), C.c_void_p]
+    lib.spatten_prefill_scratch_bytes.argtypes = [C.c_int32] * 5
+    lib.spatten_prefill_scratch_bytes.restype = C.c_int64
     lib.spatten_wait_flags.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.spatten_kv_quantize.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                         C.c_int32, C.c_int32, C.POINTER(QuantKV), C.c_int32, C.c_void_p]

@@ -20,84 +20,13 @@
 
 #include "../../include/spatten_b200.h"
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace spatten {
 
 constexpr int kUThreads = 128;     // 4 warps: producers, then epilogue (warp w owns TMEM lanes 32w..32w+31)
 constexpr int kTileM = 128;
 constexpr int kTileN = 128;
-
-// ---- tcgen05 wrappers ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  // SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48)
-  // | layout_type [61,64) = 0 (SWIZZLE_NONE / interleave)
-  return static_cast<uint64_t>((saddr >> 4) & 0x3FFFu) | (static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         (static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
-// InstrDescriptor for kind::f16: D = f32, A = B = f16, A K-major, B K-major (0) or MN-major (1), N, M
-__host__ __device__ constexpr uint32_t umma_idesc(int m, int n, int b_mn_major) {
-  return (1u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(b_mn_major) << 16) |
-         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(static_cast<uint32_t>(accumulate))
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// mbarrier wait that cannot wedge the GPU: a tensor-core commit that never arrives (a malformed descriptor) traps
-// after ~1 s instead of spinning forever
-__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 2000000000ll) __trap();
-  }
-}
-
-// byte offset of the 16-byte piece (row r, 8-element K chunk c) inside a K-major no-swizzle tile with `chunks`
-// K chunks per row: core matrix (r/8, c) at (r/8)*chunks*128 + c*128, row r%8 inside it
-__device__ __forceinline__ uint32_t kmajor_off(int r, int c, int chunks) {
-  return static_cast<uint32_t>((r >> 3) * chunks * 128 + c * 128 + (r & 7) * 16);
-}
-
-__device__ __forceinline__ float pf_div_by_const(float x, float c, float rc) {
-  const float y = x * rc;
-  const float r = fmaf(-y, c, x);
-  const float y2 = fmaf(r, rc, y);
-  return (fabsf(y2) <= 3.4028234e38f) ? y2 : y;
-}
 
 struct PrefillParams {
   const __half* q;          // [b, q_len, H, D] un-rotated
@@ -480,6 +409,16 @@ __global__ void __launch_bounds__(kColsumThreads) prob_colsum_kernel(const Prefi
 
 using namespace spatten;
 
+namespace spatten {
+int64_t prefill_fused_scratch_bytes(int batch, int H, int H_kv, int q_len, int kv_len);   // prefill_fused.cu
+int launch_prefill_fused(const SpattenPrefillArgs* a, cudaStream_t st);
+}  // namespace spatten
+
+extern "C" int64_t spatten_prefill_scratch_bytes(int32_t batch, int32_t num_heads, int32_t num_kv_heads, int32_t q_len,
+                                                 int32_t kv_len) {
+  return prefill_fused_scratch_bytes(batch, num_heads, num_kv_heads, q_len, kv_len);
+}
+
 extern "C" int spatten_prefill_attn(const SpattenPrefillArgs* a, void* stream) {
   SPATTEN_CHECK_ARG(a != nullptr && a->struct_size == sizeof(SpattenPrefillArgs), "spatten_prefill_attn: bad args/struct_size");
   SPATTEN_CHECK_ARG(a->batch > 0 && a->num_heads > 0 && a->num_kv_heads > 0 && a->num_heads % a->num_kv_heads == 0,
@@ -507,6 +446,16 @@ extern "C" int spatten_prefill_attn(const SpattenPrefillArgs* a, void* stream) {
   p.batch = a->batch; p.H = a->num_heads; p.n_rep = a->num_heads / a->num_kv_heads; p.q_len = a->q_len; p.kv_len = a->kv_len; p.rope_len = a->rope_len;
   p.sqrt_d = static_cast<float>(sqrt(static_cast<double>(a->head_dim))); p.rsqrt_d = 1.0f / p.sqrt_d;
 
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!(a->flags & SPATTEN_PREFILL_LEGACY) && a->scratch_bytes > 0) {
+    SPATTEN_CHECK_ARG((reinterpret_cast<uintptr_t>(a->probs) & 15) == 0, "spatten_prefill_attn: scratch must be 16-byte aligned");
+    if (a->scratch_bytes >= prefill_fused_scratch_bytes(a->batch, a->num_heads, a->num_kv_heads, a->q_len, a->kv_len))
+      return launch_prefill_fused(a, st);
+    SPATTEN_CHECK_ARG(a->scratch_bytes >= (static_cast<int64_t>(a->batch - 1) * a->logits_stride_b +
+                                           static_cast<int64_t>(a->num_heads - 1) * a->logits_stride_h +
+                                           static_cast<int64_t>(a->q_len - 1) * a->logits_stride_q + a->kv_len) * 2,
+                      "spatten_prefill_attn: scratch_bytes too small for either path");
+  }
   constexpr int D = 128;
   constexpr int smem_qk = 2 * kTileM * D * 2, smem_pv = kTileM * 64 * 2 + 64 * D * 2;
   static bool configured[64] = {};
@@ -518,7 +467,6 @@ extern "C" int spatten_prefill_attn(const SpattenPrefillArgs* a, void* stream) {
     if (e1 != cudaSuccess || e2 != cudaSuccess) return cuda_fail(e1 != cudaSuccess ? e1 : e2, "cudaFuncSetAttribute(umma kernels)");
     configured[dev] = true;
   }
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int mt = (a->q_len + kTileM - 1) / kTileM, nt = (a->kv_len + kTileN - 1) / kTileN, bh = a->batch * a->num_heads;
   umma_qk_kernel<D><<<dim3(nt, mt, bh), kUThreads, smem_qk, st>>>(p);
   const int64_t rows = static_cast<int64_t>(a->batch) * a->num_heads * a->q_len;

@@ -239,13 +239,15 @@ class DecodeStep:
 
 def prefill_attn(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, kv_len: int, rope: torch.Tensor,
                  q_pos: torch.Tensor, mask: Optional[torch.Tensor] = None, logits: Optional[torch.Tensor] = None,
-                 importance: Optional[torch.Tensor] = None):
+                 importance: Optional[torch.Tensor] = None, causal: bool = False, legacy: bool = False):
     """Prefill / chunk attention on the tcgen05 tensor cores -- `spatten_prefill_attn` (head_dim 128).
 
     q fp16 [b,q_len,H,D] un-rotated; the new K/V rows are already in k_cache/v_cache [b,H_kv,cap,D]; kv_len rows
-    valid; q_pos int64 [b,q_len]; mask fp16 additive [b,q_len,kv_len].  Returns (out [b,q_len,H,D],
-    logits [b,H,q_len,kv_len] == attn_scores).  `importance` fp32 [b,H,>=kv_len] accumulates the column sums of the
-    softmax probabilities (cumulative token importance) in place.
+    valid; q_pos int64 [b,q_len]; mask fp16 additive [b,q_len,kv_len] (a standard causal mask is recognised on the
+    device and turned into tile skipping); `causal=True` with mask=None applies the causal mask without a mask tensor.
+    Returns (out [b,q_len,H,D], logits [b,H,q_len,kv_len] == attn_scores).  `importance` fp32 [b,H,>=kv_len]
+    accumulates the column sums of the softmax probabilities (cumulative token importance) in place.
+    `legacy=True` runs the three-launch path (csrc/prefill_umma.cu) instead of the fused kernel.
     """
     lib = _lib.load()
     _require_cuda(q, k_cache, v_cache, rope, q_pos, mask, logits)
@@ -260,7 +262,10 @@ def prefill_attn(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, 
         logits = torch.empty((b, H, q_len, kv_len), dtype=torch.float16, device=q.device)
     if logits.stride(3) != 1:
         raise ValueError("logits last dimension must be contiguous")
-    probs = torch.empty_strided(logits.shape, logits.stride(), dtype=torch.float16, device=q.device)
+    if legacy:
+        probs = torch.empty_strided(logits.shape, logits.stride(), dtype=torch.float16, device=q.device)
+    else:       # fused path: the scratch only holds the rotated / re-tiled operand images
+        probs = torch.empty(int(lib.spatten_prefill_scratch_bytes(b, H, H_kv, q_len, int(kv_len))), dtype=torch.uint8, device=q.device)
     out = torch.empty((b, q_len, H, D), dtype=torch.float16, device=q.device)
     a = _lib.PrefillArgs()
     a.struct_size = C.sizeof(_lib.PrefillArgs)
@@ -285,6 +290,10 @@ def prefill_attn(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, 
         _require_cuda(importance)
         a.importance, a.importance_stride = importance.data_ptr(), importance.stride(1)
     a.logits_stride_b, a.logits_stride_h, a.logits_stride_q = logits.stride(0), logits.stride(1), logits.stride(2)
+    a.flags = (_lib.PREFILL_CAUSAL if causal else 0) | (_lib.PREFILL_LEGACY if legacy else 0)
+    a.scratch_bytes = 0 if legacy else probs.numel()
+    if causal and mask is not None:
+        raise ValueError("causal=True takes no mask tensor")
     with torch.cuda.device(q.device):
         _lib.check(lib.spatten_prefill_attn(C.byref(a), C.c_void_p(_stream_ptr(q.device))))
     return out, logits

@@ -109,3 +109,17 @@ def test_oracle_decode_then_prune_chain_matches_reference(c):
                       torch.arange(tail0, c.past + 1).expand(c.H, -1)], dim=1)
     rep = assert_chain_sets_match(full, g["kept_idx"], g["attn_scores"][0, :, 0], g["kth"], g["next"], c.name, slack_ulps=0)
     assert rep["identical"] + rep["boundary_flips_heads"] == c.H
+
+
+def test_single_multiply_reproduces_the_fp16_logit_division():
+    """csrc/prefill_fused.cu forms fp16(x / sqrt(128)) (modify_llama.py:111-113, fp32 opmath) as fp16(x * r) with
+    r = nextafter(fl32(1/sqrt(128)), 1): exhaustive over every finite fp16 x.  The plain reciprocal misses 52 values."""
+    import numpy as np
+    h = np.arange(65536, dtype=np.uint32).astype(np.uint16).view(np.float16)
+    h = h[np.isfinite(h)]
+    c = np.float32(np.sqrt(np.float32(128.0)))
+    ref = (h.astype(np.float32) / c).astype(np.float16)
+    r0 = np.float32(1.0) / c
+    r_up = np.nextafter(r0, np.float32(1.0), dtype=np.float32)
+    assert ((h.astype(np.float32) * r_up).astype(np.float16).view(np.uint16) == ref.view(np.uint16)).all()
+    assert ((h.astype(np.float32) * r0).astype(np.float16).view(np.uint16) != ref.view(np.uint16)).sum() == 52

@@ -113,3 +113,101 @@ def test_prefill_importance_column_sums(b, H, past, q_len):
     ops.prefill_attn(*args, importance=imp)
     torch.cuda.synchronize()
     assert torch.allclose(imp[..., :kv].cpu(), 2 * ref, rtol=2e-3, atol=4e-4)
+
+
+# ---- fused single-kernel path (csrc/prefill_fused.cu) vs the three-launch path and the oracle -------------------------
+
+def _rand_case(b, H, H_kv, past, q_len, seed):
+    D, kv = 128, past + q_len
+    q = det_normal((b, H, q_len, D), seed, 1.0, torch.float16)
+    k = det_normal((b, H_kv, kv, D), seed + 1, 1.0, torch.float16)
+    v = det_normal((b, H_kv, kv, D), seed + 2, 1.0, torch.float16)
+    pos = torch.arange(past, kv).unsqueeze(0).expand(b, q_len).contiguous()
+    return q, k, v, pos, kv
+
+
+@pytest.mark.parametrize("b,H,H_kv,past,q_len", [(1, 4, 4, 0, 128), (1, 4, 4, 0, 300), (2, 4, 2, 130, 257), (1, 2, 2, 1000, 129),
+                                                 (1, 2, 1, 0, 1024), (1, 1, 1, 77, 16)])
+def test_fused_prefill_equals_three_launch_path(b, H, H_kv, past, q_len):
+    """Same logits bit for bit (both form fp16(fp16(acc)/sqrt(D)) from the same tensor-core accumulation order), same
+    output within the parity bar, same importance column sums."""
+    from spatten_b200 import ops
+    dev = "cuda"
+    q, k, v, pos, kv = _rand_case(b, H, H_kv, past, q_len, 9100 + past + q_len)
+    mask = causal_mask(b, q_len, past, torch.float16)[:, 0].contiguous().to(dev)
+    args = (q.transpose(1, 2).contiguous().to(dev), k.to(dev), v.to(dev), kv, ops.rope_table(128, kv, dev), pos.to(dev), mask)
+    imp_f = torch.zeros((b, H, kv + 5), dtype=torch.float32, device=dev)
+    imp_l = torch.zeros_like(imp_f)
+    out_f, lg_f = ops.prefill_attn(*args, importance=imp_f)
+    out_l, lg_l = ops.prefill_attn(*args, importance=imp_l, legacy=True)
+    torch.cuda.synchronize()
+    assert torch.equal(lg_f.view(torch.int16), lg_l.view(torch.int16))
+    assert rel_err(out_f.cpu(), out_l.cpu()) <= OUT_REL_TOL
+    assert torch.allclose(imp_f, imp_l, rtol=2e-3, atol=2e-4)
+    assert (imp_f[..., kv:] == 0).all()
+
+
+def test_fused_prefill_causal_flag_equals_causal_mask_tensor():
+    from spatten_b200 import ops
+    dev = "cuda"
+    b, H, H_kv, past, q_len = 2, 4, 4, 200, 333
+    q, k, v, pos, kv = _rand_case(b, H, H_kv, past, q_len, 9300)
+    mask = causal_mask(b, q_len, past, torch.float16)[:, 0].contiguous().to(dev)
+    base = (q.transpose(1, 2).contiguous().to(dev), k.to(dev), v.to(dev), kv, ops.rope_table(128, kv, dev), pos.to(dev))
+    out_m, lg_m = ops.prefill_attn(*base, mask)
+    out_c, lg_c = ops.prefill_attn(*base, None, causal=True)
+    torch.cuda.synchronize()
+    assert torch.equal(lg_m, lg_c) and torch.equal(out_m, out_c)
+
+
+@pytest.mark.parametrize("kind", ["none", "padding", "random"])
+def test_fused_prefill_generic_masks_vs_oracle(kind):
+    """A mask that is not the standard causal one takes the element-wise path (:127-132): no mask, a left-padding mask
+    on top of the causal one, and an arbitrary 0 / -inf / finite pattern."""
+    import math
+    from spatten_b200 import ops
+    dev = "cuda"
+    b, H, past, q_len, D = 2, 2, 60, 200, 128
+    q, k, v, pos, kv = _rand_case(b, H, H, past, q_len, 9400)
+    if kind == "none":
+        mask = None
+    else:
+        mask = causal_mask(b, q_len, past, torch.float16).clone()
+        if kind == "padding":
+            mask[1, :, :, :37] = torch.finfo(torch.float16).min
+        else:
+            r = det_normal((b, 1, q_len, kv), 9401, 1.0, torch.float32)
+            mask = torch.where(r > 0.8, torch.full_like(mask, float("-inf")), mask)
+            mask = torch.where((r < -0.8) & (mask == 0), torch.full_like(mask, -3.0), mask)
+            mask[:, :, :, 0] = 0                                    # no fully masked rows
+    cos, sin = O.rotary_tables(D, kv, torch.float16)
+    q_rot = O.rope_single(q, cos, sin, pos)
+    k_rot = O.rope_single(k, cos, sin, torch.arange(kv).unsqueeze(0).expand(b, kv))
+    ref_scores = torch.matmul(q_rot, k_rot.transpose(2, 3)) / math.sqrt(D)
+    s = ref_scores if mask is None else ref_scores + mask
+    probs32 = torch.softmax(s.float(), dim=-1)
+    ref_out = torch.matmul(probs32.to(torch.float16), v)
+    imp = torch.zeros((b, H, kv), dtype=torch.float32, device=dev)
+    out, logits = ops.prefill_attn(q.transpose(1, 2).contiguous().to(dev), k.to(dev), v.to(dev), kv, ops.rope_table(D, kv, dev),
+                                   pos.to(dev), None if mask is None else mask[:, 0].contiguous().to(dev), importance=imp)
+    torch.cuda.synchronize()
+    assert_logits_close(logits.cpu(), ref_scores, kind)
+    assert rel_err(out.cpu(), ref_out.transpose(1, 2)) <= OUT_REL_TOL
+    assert torch.allclose(imp.cpu(), probs32.sum(2), rtol=2e-3, atol=2e-4)
+
+
+def test_fused_prefill_unaligned_logit_strides():
+    """kv_len not a multiple of 8 (scalar logit stores) and a logits buffer with a padded row pitch."""
+    from spatten_b200 import ops
+    dev = "cuda"
+    b, H, past, q_len = 1, 2, 3, 250
+    q, k, v, pos, kv = _rand_case(b, H, H, past, q_len, 9500)
+    mask = causal_mask(b, q_len, past, torch.float16)[:, 0].contiguous().to(dev)
+    args = (q.transpose(1, 2).contiguous().to(dev), k.to(dev), v.to(dev), kv, ops.rope_table(128, kv, dev), pos.to(dev), mask)
+    out_a, lg_a = ops.prefill_attn(*args)
+    big = torch.full((b, H, q_len, kv + 11), 7.0, dtype=torch.float16, device=dev)
+    out_b, lg_b = ops.prefill_attn(*args, logits=big[..., :kv])
+    out_l, lg_l = ops.prefill_attn(*args, legacy=True)
+    torch.cuda.synchronize()
+    assert torch.equal(lg_a, lg_l) and torch.equal(lg_b, lg_l) and (big[..., kv:] == 7.0).all()
+    assert torch.equal(out_a, out_b) and rel_err(out_a.cpu(), out_l.cpu()) <= OUT_REL_TOL

@@ -195,20 +195,25 @@ def bench_prefill(iters, sizes=(1024, 4096, 8192)):
         pos = torch.arange(S, device=dev).unsqueeze(0)
         mask = torch.full((S, S), torch.finfo(torch.float16).min, dtype=torch.float16, device=dev).triu(1)[None].contiguous()
         logits = torch.empty((b, H, S, S), dtype=torch.float16, device=dev)
-        for _ in range(2):
-            ops.prefill_attn(q, kc, vc, S, rope, pos, mask, logits)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n_it = max(2, iters // 10)
-        e0.record()
-        for _ in range(n_it):
-            ops.prefill_attn(q, kc, vc, S, rope, pos, mask, logits)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / n_it
-        flops = 4.0 * S * S * H * D * b                      # both matmuls, dense (the reference computes the full square)
-        print(json.dumps({"kind": "prefill_umma", "S": S, "H": H, "ms_per_layer": round(ms, 3),
-                          "TFLOPs": round(flops / ms / 1e9, 1), "logits_GB": round(b * H * S * S * 2 / 1e9, 2)}), flush=True)
+        imp = torch.zeros((b, H, S), dtype=torch.float32, device=dev)
+        for name, kw in (("fused", {}), ("fused+importance", {"importance": imp}), ("fused causal flag", {"causal": True}),
+                         ("three-launch", {"legacy": True})):
+            m = None if kw.get("causal") else mask
+            for _ in range(2):
+                ops.prefill_attn(q, kc, vc, S, rope, pos, m, logits, **kw)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_it = max(2, iters // 10)
+            e0.record()
+            for _ in range(n_it):
+                ops.prefill_attn(q, kc, vc, S, rope, pos, m, logits, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n_it
+            flops = 4.0 * S * S * H * D * b                  # both matmuls, dense (the reference computes the full square)
+            print(json.dumps({"kind": "prefill", "path": name, "S": S, "H": H, "ms_per_layer": round(ms, 3),
+                              "dense_equiv_TFLOPs": round(flops / ms / 1e9, 1), "logits_GB": round(b * H * S * S * 2 / 1e9, 2),
+                              "logits_write_GBps": round(b * H * S * S * 2 / ms / 1e6, 1)}), flush=True)
 
 
 def timeline(b, H, D, n, L, flags=0):
