@@ -8,8 +8,8 @@
 //                            IMAGES -- the exact shared-memory byte order the tensor core reads (8x8 core matrices, no
 //                            swizzle) -- so the main kernel feeds its rings with one contiguous 32 KiB bulk copy (TMA
 //                            engine, SASS UBLKCP) per tile and no CUDA-core staging.
-//   1. prefill_fused_kernel  320 threads: warps 0-7 = two softmax groups (group g owns TMEM buffer S[g] and P buffer g,
-//                            thread = query row), warp 8 = loader, warp 9 = MMA issuer.
+//   1. prefill_fused_kernel  576 threads: warps 0-15 = two softmax groups (group g owns TMEM buffer S[g] and P buffer g,
+//                            two threads per query row), warp 16 = loaders (K lane, V lane), warp 17 = MMA issuer.
 //        phase A  for every key tile j:      S[j&1] = Q.K_j^T (tcgen05)  ->  fp16 logits written ONCE (coalesced through a
 //                                            shared-memory staging tile); running row max / row sum (online) for the tiles
 //                                            the mask leaves alive.  HBM-bound: 32 KiB of logits per tile.
@@ -34,7 +34,9 @@ namespace spatten {
 constexpr int kFT = 128;                       // tile edge: queries x keys
 constexpr int kFD = 128;                       // head_dim
 constexpr int kImgBytes = kFT * kFD * 2;       // 32 KiB operand image
-constexpr int kFusedThreads = 320;
+constexpr int kGroupThreads = 256;                // one softmax group: 8 warps, two threads per query row
+constexpr int kLoadWarp = 16, kMmaWarp = 17;
+constexpr int kFusedThreads = 18 * 32;
 constexpr int kStagePitch = kFT * 2 + 16;      // bytes; logits staging row pitch (16-byte stores of 8 rows hit 8 bank groups)
 constexpr int kStageBytes = kFT * kStagePitch; // 34816
 constexpr int kOffQ = 0, kOffK = kImgBytes, kOffV = 3 * kImgBytes, kOffP = 5 * kImgBytes, kOffBars = 7 * kImgBytes;
@@ -196,17 +198,17 @@ __global__ void __launch_bounds__(kFusedThreads, 1) prefill_fused_kernel(const F
   const int m0 = mtile * kFT;
   const int off = p.kv_len - p.q_len;
 
-  if (warp == 8) tmem_alloc(sTmem, 512);                                   // S[0], S[1], O: 3 x 128 columns
-  if (tid == 9 * 32) {
+  if (warp == kLoadWarp) tmem_alloc(sTmem, 512);                           // S[0], S[1], O: 3 x 128 columns
+  if (tid == kMmaWarp * 32) {
     mbar_init(&bars[Q_FULL], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars[K_FULL + i], 1);  mbar_init(&bars[K_EMPTY + i], 1);
       mbar_init(&bars[V_FULL + i], 1);  mbar_init(&bars[V_EMPTY + i], 1);
-      mbar_init(&bars[S_FULL + i], 1);  mbar_init(&bars[S_EMPTY + i], 128);
-      mbar_init(&bars[P_FULL + i], 128); mbar_init(&bars[P_EMPTY + i], 1);
+      mbar_init(&bars[S_FULL + i], 1);  mbar_init(&bars[S_EMPTY + i], kGroupThreads);
+      mbar_init(&bars[P_FULL + i], kGroupThreads); mbar_init(&bars[P_EMPTY + i], 1);
     }
     mbar_init(&bars[O_FULL], 1);
-    mbar_init(&bars[A_DONE], 8);
+    mbar_init(&bars[A_DONE], 2 * kGroupThreads / 32);
     fence_mbar_init();
   }
   int mode = p.mode;
@@ -220,28 +222,24 @@ __global__ void __launch_bounds__(kFusedThreads, 1) prefill_fused_kernel(const F
   const int nt = p.nt;
   const int nb = mode == 1 ? min(nt, (last_row + off) / kFT + 1) : nt;      // key tiles the mask leaves alive
 
-  if (warp == 8) {
-    // ===== loader: contiguous 32 KiB images through the TMA engine =====
+  if (warp == kLoadWarp) {
+    // ===== loaders: contiguous 32 KiB images through the TMA engine; lane 0 feeds Q and the K ring, lane 1 the V ring =====
+    const uint64_t keep = policy_evict_last();                             // K / V images are re-read by every query tile of the head
+    const int64_t kv_img0 = (static_cast<int64_t>(b) * (p.H / p.n_rep) + kvh) * nt * kImgBytes;
     if (lane == 0) {
-      const uint64_t keep = policy_evict_last();                           // K / V images are re-read by every query tile of the head
-      const uint64_t once = policy_evict_first();
-      const uint8_t* kimg = p.k_img + (static_cast<int64_t>(b) * (p.H / p.n_rep) + kvh) * nt * kImgBytes;
-      const uint8_t* vimg = p.v_img + (static_cast<int64_t>(b) * (p.H / p.n_rep) + kvh) * nt * kImgBytes;
+      const uint8_t* kimg = p.k_img + kv_img0;
       mbar_expect_tx(&bars[Q_FULL], kImgBytes);
-      bulk_g2s(sQ, p.q_img + (static_cast<int64_t>(bh) * p.mt + mtile) * kImgBytes, kImgBytes, &bars[Q_FULL], once);
-      uint32_t kuse = 0;
-      for (int j = 0; j < nt; ++j, ++kuse) {
-        const int s = kuse & 1;
+      bulk_g2s(sQ, p.q_img + (static_cast<int64_t>(bh) * p.mt + mtile) * kImgBytes, kImgBytes, &bars[Q_FULL], policy_evict_first());
+      for (int kuse = 0; kuse < nt + nb; ++kuse) {
+        const int s = kuse & 1, j = kuse < nt ? kuse : kuse - nt;
         mbar_wait_bounded(&bars[K_EMPTY + s], ((kuse >> 1) & 1) ^ 1);
         mbar_expect_tx(&bars[K_FULL + s], kImgBytes);
         bulk_g2s(sK + s * kImgBytes, kimg + static_cast<int64_t>(j) * kImgBytes, kImgBytes, &bars[K_FULL + s], keep);
       }
-      for (int j = 0; j < nb; ++j, ++kuse) {
-        const int s = kuse & 1;
-        mbar_wait_bounded(&bars[K_EMPTY + s], ((kuse >> 1) & 1) ^ 1);
-        mbar_expect_tx(&bars[K_FULL + s], kImgBytes);
-        bulk_g2s(sK + s * kImgBytes, kimg + static_cast<int64_t>(j) * kImgBytes, kImgBytes, &bars[K_FULL + s], keep);
-        if (j == 0) mbar_wait_bounded(&bars[A_DONE], 0);                   // the V ring doubles as phase A's logits staging
+    } else if (lane == 1) {
+      const uint8_t* vimg = p.v_img + kv_img0;
+      mbar_wait_bounded(&bars[A_DONE], 0);                                 // the V ring doubles as phase A's logits staging
+      for (int j = 0; j < nb; ++j) {
         const int vs = j & 1;
         mbar_wait_bounded(&bars[V_EMPTY + vs], ((j >> 1) & 1) ^ 1);
         mbar_expect_tx(&bars[V_FULL + vs], kImgBytes);
@@ -249,26 +247,26 @@ __global__ void __launch_bounds__(kFusedThreads, 1) prefill_fused_kernel(const F
       }
     }
     __syncwarp();
-  } else if (warp == 9) {
+  } else if (warp == kMmaWarp) {
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc_qk = umma_idesc(kFT, kFT, 0);
       constexpr uint32_t idesc_pv = umma_idesc(kFT, kFD, 1);
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
       mbar_wait_bounded(&bars[Q_FULL], 0);
-      uint32_t kuse = 0, jt = 0;
+      uint32_t jt = 0;                                                     // S tiles issued so far: K slot = S slot = jt & 1
       auto issue_qk = [&]() {
-        const int s = kuse & 1, sb = jt & 1;
-        mbar_wait_bounded(&bars[K_FULL + s], (kuse >> 1) & 1);
-        mbar_wait_bounded(&bars[S_EMPTY + sb], ((jt >> 1) & 1) ^ 1);
+        const int s = jt & 1;
+        mbar_wait_bounded(&bars[K_FULL + s], (jt >> 1) & 1);
+        mbar_wait_bounded(&bars[S_EMPTY + s], ((jt >> 1) & 1) ^ 1);
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < kFD / 16; ++ks)
-          umma_f16(tmem + sb * kFT, umma_desc(aQ + ks * 256, 128, 2048), umma_desc(aK + s * kImgBytes + ks * 256, 128, 2048),
+          umma_f16(tmem + s * kFT, umma_desc(aQ + ks * 256, 128, 2048), umma_desc(aK + s * kImgBytes + ks * 256, 128, 2048),
                    idesc_qk, ks > 0);
         umma_commit(&bars[K_EMPTY + s]);
-        umma_commit(&bars[S_FULL + sb]);
-        ++kuse; ++jt;
+        umma_commit(&bars[S_FULL + s]);
+        ++jt;
       };
       auto issue_pv = [&](int j) {
         const int g = (nt + j) & 1, vs = j & 1;
@@ -283,20 +281,24 @@ __global__ void __launch_bounds__(kFusedThreads, 1) prefill_fused_kernel(const F
         umma_commit(&bars[V_EMPTY + vs]);
       };
       for (int j = 0; j < nt; ++j) issue_qk();
+      // phase B: S of tile j + 2 is issued as soon as its group has drained S of tile j into registers, i.e. while that
+      // group is still busy with the exponentials of tile j
+      issue_qk();
+      if (nb > 1) issue_qk();
       for (int j = 0; j < nb; ++j) {
-        issue_qk();
-        if (j > 0) issue_pv(j - 1);
+        if (j + 2 < nb) issue_qk();
+        issue_pv(j);
       }
-      issue_pv(nb - 1);
       umma_commit(&bars[O_FULL]);
     }
     __syncwarp();
   } else {
-    // ===== softmax groups: thread = query row (TMEM lane), group g drains S[g] =====
-    const int g = warp >> 2, quarter = warp & 3, row = quarter * 32 + lane;
+    // ===== softmax groups: group g drains S[g]; two threads per query row (TMEM lane), 64 key columns each =====
+    const int g = warp >> 3, wg = warp & 7, quarter = warp & 3, half = (warp >> 2) & 1, row = quarter * 32 + lane;
+    const int col0 = half * 64;
     const int row_g = m0 + row;                                            // query index inside the chunk
     const bool row_ok = row_g < p.q_len;
-    const uint32_t t_s = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + g * kFT;
+    const uint32_t t_s = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + g * kFT + col0;
     const int row_lim = (mode == 1 ? min(row_g + off, p.kv_len - 1) : p.kv_len - 1);   // last live key of this row
     const __half* mrow = (mode == 0 && row_ok) ? p.mask + (static_cast<int64_t>(b) * p.q_len + row_g) * p.kv_len : nullptr;
     uint8_t* stage = sV + g * kStageBytes;
@@ -304,137 +306,175 @@ __global__ void __launch_bounds__(kFusedThreads, 1) prefill_fused_kernel(const F
     const bool vec_ok = (p.ls_q % 8) == 0 && ((reinterpret_cast<uintptr_t>(lbase) & 15) == 0);
     uint32_t suse = 0;
     float m = -CUDART_INF_F, l = 0.f;
+    __half2 lg[32];                                                        // this thread's 64 logits of the current tile
 
-    // ---- phase A: logits + row statistics ----
-    for (int j = g; j < nt; j += 2, ++suse) {
-      const int n0 = j * kFT;
+    // S[g] -> fp16 logits in registers, then the buffer goes straight back to the MMA issuer
+    auto drain_s = [&]() {
       mbar_wait_bounded(&bars[S_FULL + g], suse & 1);
+      ++suse;
       tc_fence_after();
-      const bool stats = j < nb && row_ok;
-#pragma unroll 1
-      for (int cb = 0; cb < kFT; cb += 32) {
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
         float v[32];
-        tmem_ld32(t_s + cb, v);
-        __align__(16) __half2 o[16];
+        tmem_ld32(t_s + c2 * 32, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) o[i] = logit2(v[2 * i], v[2 * i + 1], p.rs_up);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          *reinterpret_cast<uint4*>(stage + row * kStagePitch + cb * 2 + i * 16) = reinterpret_cast<const uint4*>(o)[i];
-        const int lim = row_lim - n0 - cb;                                 // columns 0..lim of this chunk are live
-        if (stats && lim >= 0) {
-          float x[32];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            __half2 t = o[i];
-            if (mrow) t = __hadd2_rn(t, mask2(mrow + n0 + cb, i, lim));                  // fp16 add, as attn_weights + attention_mask (:132)
-            const float2 f = __half22float2(t);
-            x[2 * i] = f.x; x[2 * i + 1] = f.y;
-          }
-          if (lim < 31) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) if (i > lim) x[i] = -CUDART_INF_F;
-          }
-          float cm = x[0];
-#pragma unroll
-          for (int i = 1; i < 32; ++i) cm = fmaxf(cm, x[i]);
-          if (cm > m) { l *= fast_exp2((m - cm) * kLog2e); m = cm; }      // m = -inf: l is 0 and stays 0
-          if (m > -CUDART_INF_F) {
-            const float ml2 = m * kLog2e;
-            float part = 0.f;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) part += fast_exp2(fmaf(x[i], kLog2e, -ml2));
-            l += part;
-          }
-        }
+        for (int i = 0; i < 16; ++i) lg[c2 * 16 + i] = logit2(v[2 * i], v[2 * i + 1], p.rs_up);
       }
       tc_fence_before();
       mbar_arrive(&bars[S_EMPTY + g]);
-      group_sync(1 + g, 128);
-      {
-        const int half_w = lane >> 4, piece = lane & 15;                  // 2 rows per warp instruction, 16 pieces of 8 logits
-        const int col = piece * 8;
-#pragma unroll 4
-        for (int rr = quarter * 2 + half_w; rr < kFT; rr += 8) {
-          const int grow = m0 + rr;
-          if (grow >= p.q_len || n0 + col >= p.kv_len) continue;
-          const uint4 val = *reinterpret_cast<const uint4*>(stage + rr * kStagePitch + col * 2);
-          __half* dst = lbase + static_cast<int64_t>(grow) * p.ls_q + n0 + col;
-          if (vec_ok && n0 + col + 8 <= p.kv_len) {
-            __stcs(reinterpret_cast<uint4*>(dst), val);
-          } else {
-            const __half* hv = reinterpret_cast<const __half*>(&val);
-            for (int i = 0; i < 8; ++i)
-              if (n0 + col + i < p.kv_len) dst[i] = hv[i];
+    };
+
+    // ---- phase A: logits + row statistics ----
+    for (int j = g; j < nt; j += 2) {
+      const int n0 = j * kFT;
+      drain_s();
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<uint4*>(stage + row * kStagePitch + (col0 + i * 8) * 2) = *reinterpret_cast<const uint4*>(&lg[4 * i]);
+      const int lim = row_lim - n0 - col0;                                 // columns 0..lim of this thread's 64 are live
+      if (j < nb && row_ok && lim >= 0) {
+        if (lim >= 63 && mrow == nullptr) {
+          __half2 hm = lg[0];
+#pragma unroll
+          for (int i = 1; i < 32; ++i) hm = __hmax2(hm, lg[i]);
+          const float cm = fmaxf(__low2float(hm), __high2float(hm));
+          if (cm > m) { l *= fast_exp2((m - cm) * kLog2e); m = cm; }      // m = -inf: l is 0 and stays 0
+          const float ml2 = m * kLog2e;
+          float part0 = 0.f, part1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float2 f = __half22float2(lg[i]);
+            part0 += fast_exp2(fmaf(f.x, kLog2e, -ml2));
+            part1 += fast_exp2(fmaf(f.y, kLog2e, -ml2));
+          }
+          l += part0 + part1;
+        } else {
+#pragma unroll
+          for (int cb = 0; cb < 64; cb += 16) {
+            if (cb > lim) break;
+            float x[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __half2 t = lg[(cb >> 1) + i];
+              if (mrow) t = __hadd2_rn(t, mask2(mrow + n0 + col0 + cb, i, lim - cb));   // fp16 add, as attn_weights + attention_mask (:132)
+              const float2 f = __half22float2(t);
+              x[2 * i] = (cb + 2 * i <= lim) ? f.x : -CUDART_INF_F;
+              x[2 * i + 1] = (cb + 2 * i + 1 <= lim) ? f.y : -CUDART_INF_F;
+            }
+            float cm = x[0];
+#pragma unroll
+            for (int i = 1; i < 16; ++i) cm = fmaxf(cm, x[i]);
+            if (cm > m) { l *= fast_exp2((m - cm) * kLog2e); m = cm; }
+            if (m > -CUDART_INF_F) {
+              const float ml2 = m * kLog2e;
+              float part = 0.f;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) part += fast_exp2(fmaf(x[i], kLog2e, -ml2));
+              l += part;
+            }
           }
         }
       }
-      group_sync(1 + g, 128);
+      group_sync(1 + g, kGroupThreads);
+      {
+        const int half_w = lane >> 4, piece = lane & 15;                  // 2 rows per warp instruction, 16 pieces of 8 logits
+        const int r0 = wg * 2 + half_w, col = piece * 8;
+        const uint8_t* src = stage + r0 * kStagePitch + col * 2;
+        __half* dst = lbase + static_cast<int64_t>(m0 + r0) * p.ls_q + n0 + col;
+        if (vec_ok && m0 + kFT <= p.q_len && n0 + kFT <= p.kv_len) {
+#pragma unroll
+          for (int it = 0; it < kFT / 16; ++it)
+            __stcs(reinterpret_cast<uint4*>(dst + static_cast<int64_t>(it) * 16 * p.ls_q),
+                   *reinterpret_cast<const uint4*>(src + it * 16 * kStagePitch));
+        } else {
+#pragma unroll 1
+          for (int it = 0; it < kFT / 16; ++it) {
+            const int grow = m0 + r0 + it * 16;
+            if (grow >= p.q_len || n0 + col >= p.kv_len) continue;
+            const uint4 val = *reinterpret_cast<const uint4*>(src + it * 16 * kStagePitch);
+            __half* d = dst + static_cast<int64_t>(it) * 16 * p.ls_q;
+            if (vec_ok && n0 + col + 8 <= p.kv_len) {
+              __stcs(reinterpret_cast<uint4*>(d), val);
+            } else {
+              const __half* hv = reinterpret_cast<const __half*>(&val);
+              for (int i = 0; i < 8; ++i)
+                if (n0 + col + i < p.kv_len) d[i] = hv[i];
+            }
+          }
+        }
+      }
+      group_sync(1 + g, kGroupThreads);
     }
-    // staging is dead from here on: release the V ring to the loader, then merge the two groups' statistics
-    sStats[g * kFT + row] = make_float2(m, l);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&bars[A_DONE]);
-    group_sync(3, 256);
+    // merge the statistics: the two column halves of a row inside the group (through the dead staging tile), then the
+    // two groups; the staging region is released to the V loader in between
     {
-      const float2 o2 = sStats[(g ^ 1) * kFT + row];
-      const float M = fmaxf(m, o2.x);
+      float2* xch = reinterpret_cast<float2*>(stage);
+      if (half == 1) xch[row] = make_float2(m, l);
+      group_sync(1 + g, kGroupThreads);
+      if (half == 0) {
+        const float2 o2 = xch[row];
+        const float M = fmaxf(m, o2.x);
+        if (M > -CUDART_INF_F) { l = l * fast_exp2((m - M) * kLog2e) + o2.y * fast_exp2((o2.x - M) * kLog2e); m = M; }
+        sStats[g * kFT + row] = make_float2(m, l);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[A_DONE]);
+      group_sync(3, 2 * kGroupThreads);
+      const float2 s0 = sStats[row], s1 = sStats[kFT + row];
+      const float M = fmaxf(s0.x, s1.x);
       if (M > -CUDART_INF_F) {
-        l = l * fast_exp2((m - M) * kLog2e) + o2.y * fast_exp2((o2.x - M) * kLog2e);
+        l = s0.y * fast_exp2((s0.x - M) * kLog2e) + s1.y * fast_exp2((s1.x - M) * kLog2e);
         m = M;
       } else {
         m = 0.f; l = 1.f;                                                  // fully masked row (generic mask only)
       }
     }
-    const float ml2 = m * kLog2e, inv_l = row_ok ? 1.f / l : 0.f;          // padding rows contribute nothing to the column sums
+    // p = exp2(x * log2e - sub): 1 / L folded into the exponent; padding rows get p = 0 (nothing for the column sums)
+    const float sub_l2 = row_ok ? fmaf(m, kLog2e, __log2f(l)) : CUDART_INF_F;
 
     // ---- phase B: P = exp(S - M) / L -> shared memory -> O += P.V, column sums ----
     uint8_t* pimg = sP + g * kImgBytes;
     float* imp = p.importance ? p.importance + (static_cast<int64_t>(b) * p.H + h) * p.imp_stride : nullptr;
     uint32_t puse = 0;
-    for (int j = (g + nt) & 1; j < nb; j += 2, ++suse, ++puse) {
+    for (int j = (g + nt) & 1; j < nb; j += 2, ++puse) {
       const int n0 = j * kFT;
-      mbar_wait_bounded(&bars[S_FULL + g], suse & 1);
-      tc_fence_after();
-      mbar_wait_bounded(&bars[P_EMPTY + g], (puse & 1) ^ 1);               // P.V of this group's previous tile has read the buffer
-#pragma unroll 1
-      for (int cb = 0; cb < kFT; cb += 32) {
-        float v[32];
-        tmem_ld32(t_s + cb, v);
-        const int lim = row_lim - n0 - cb;
-        __align__(16) __half2 o[16];
+      drain_s();
+      const int lim = row_lim - n0 - col0;
+      if (lim >= 63 && mrow == nullptr) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          __half2 t = logit2(v[2 * i], v[2 * i + 1], p.rs_up);
-          if (mrow) t = __hadd2_rn(t, mask2(mrow + n0 + cb, i, lim));
-          const float2 f = __half22float2(t);
-          float p0 = fast_exp2(fmaf(f.x, kLog2e, -ml2)) * inv_l;
-          float p1 = fast_exp2(fmaf(f.y, kLog2e, -ml2)) * inv_l;
-          if (lim < 31) {
-            if (2 * i > lim) p0 = 0.f;
-            if (2 * i + 1 > lim) p1 = 0.f;
-          }
-          o[i] = __floats2half2_rn(p0, p1);
+        for (int i = 0; i < 32; ++i) {
+          const float2 f = __half22float2(lg[i]);
+          lg[i] = __floats2half2_rn(fast_exp2(fmaf(f.x, kLog2e, -sub_l2)), fast_exp2(fmaf(f.y, kLog2e, -sub_l2)));
         }
+      } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          *reinterpret_cast<uint4*>(pimg + img_off(row, (cb >> 3) + i)) = reinterpret_cast<const uint4*>(o)[i];
+        for (int i = 0; i < 32; ++i) {
+          __half2 t = lg[i];
+          if (mrow) t = __hadd2_rn(t, mask2(mrow + n0 + col0, i, lim));
+          const float2 f = __half22float2(t);
+          const float p0 = 2 * i <= lim ? fast_exp2(fmaf(f.x, kLog2e, -sub_l2)) : 0.f;
+          const float p1 = 2 * i + 1 <= lim ? fast_exp2(fmaf(f.y, kLog2e, -sub_l2)) : 0.f;
+          lg[i] = __floats2half2_rn(p0, p1);
+        }
       }
-      tc_fence_before();
-      mbar_arrive(&bars[S_EMPTY + g]);
+      mbar_wait_bounded(&bars[P_EMPTY + g], (puse & 1) ^ 1);               // P.V of this group's previous tile has read the buffer
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<uint4*>(pimg + img_off(row, half * 8 + i)) = *reinterpret_cast<const uint4*>(&lg[4 * i]);
       fence_proxy_async();                                                 // generic-proxy writes -> visible to the tensor core
       mbar_arrive(&bars[P_FULL + g]);
       if (imp) {
-        group_sync(1 + g, 128);
-        // column sums of the tile just written: thread (chunk c, sub) adds rows sub, sub + 8, ... of 8 columns
-        const int c = row >> 3, sub = row & 7;
+        group_sync(1 + g, kGroupThreads);
+        // column sums of the tile just written: thread (chunk c, part hp, sub) adds rows sub + 8i, i in [8hp, 8hp + 8), of
+        // the 8 columns of chunk c; the 8 x 2 lanes that share a chunk then reduce-scatter
+        const int tg = wg * 32 + lane, c = tg >> 4, hp = (tg >> 3) & 1, sub = tg & 7;
         float acc[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] = 0.f;
         const __half2 one = __floats2half2_rn(1.f, 1.f);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const uint4 x = *reinterpret_cast<const uint4*>(pimg + i * 2048 + c * 128 + sub * 16);
+        for (int i = 0; i < 8; ++i) {
+          const uint4 x = *reinterpret_cast<const uint4*>(pimg + (hp * 8 + i) * 2048 + c * 128 + sub * 16);
           const __half2* h2 = reinterpret_cast<const __half2*>(&x);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -442,7 +482,6 @@ __global__ void __launch_bounds__(kFusedThreads, 1) prefill_fused_kernel(const F
             acc[2 * e + 1] = fhfma_hi(h2[e], one, acc[2 * e + 1]);
           }
         }
-        // reduce-scatter over the 8 lanes that share a chunk: lane `sub` ends up with column c*8 + sub
         float a4[4], a2[2];
         {
           const bool hi = sub & 4;
@@ -465,34 +504,32 @@ __global__ void __launch_bounds__(kFusedThreads, 1) prefill_fused_kernel(const F
         const bool hi1 = sub & 1;
         const float send = hi1 ? a2[0] : a2[1];
         const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-        const float total = (hi1 ? a2[1] : a2[0]) + recv;
+        float total = (hi1 ? a2[1] : a2[0]) + recv;                        // column c*8 + sub over this lane's 64 rows
+        total += __shfl_xor_sync(0xffffffffu, total, 8);                   // + the other 64 rows
         const int col = n0 + c * 8 + sub;
-        if (col < p.kv_len && total != 0.f) atomicAdd(imp + col, total);
-        group_sync(1 + g, 128);                                            // nobody overwrites P[g] while a neighbour still sums it
+        if (hp == 0 && col < p.kv_len && total != 0.f) atomicAdd(imp + col, total);
+        group_sync(1 + g, kGroupThreads);                                  // nobody overwrites P[g] while a neighbour still sums it
       }
     }
 
-    // ---- O: TMEM -> fp16 -> out[b, q, h, :]; group g writes head_dim columns [64g, 64g + 64) ----
+    // ---- O: TMEM -> fp16 -> out[b, q, h, :]; thread (group g, half) writes head_dim columns [32(2g + half), +32) ----
     mbar_wait_bounded(&bars[O_FULL], 0);
     tc_fence_after();
-    const uint32_t t_o = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + 2 * kFT + g * 64;
-    __half* dst = p.out + ((static_cast<int64_t>(b) * p.q_len + row_g) * p.H + h) * kFD + g * 64;
-#pragma unroll 1
-    for (int cb = 0; cb < 64; cb += 32) {
-      float v[32];
-      tmem_ld32(t_o + cb, v);
-      if (row_ok) {
-        __align__(16) __half2 o[16];
+    const int oc = (g * 2 + half) * 32;
+    float v[32];
+    tmem_ld32(tmem + (static_cast<uint32_t>(quarter * 32) << 16) + 2 * kFT + oc, v);
+    if (row_ok) {
+      __half* dst = p.out + ((static_cast<int64_t>(b) * p.q_len + row_g) * p.H + h) * kFD + oc;
+      __align__(16) __half2 o[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) o[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+      for (int i = 0; i < 16; ++i) o[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(dst + cb)[i] = reinterpret_cast<const uint4*>(o)[i];
-      }
+      for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(o)[i];
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 512);
+  if (warp == kLoadWarp) tmem_dealloc(tmem, 512);
 }
 
 int64_t prefill_fused_scratch_bytes(int batch, int H, int H_kv, int q_len, int kv_len) {
