@@ -10,8 +10,8 @@
 //                            engine, SASS UBLKCP) per tile and no CUDA-core staging.
 //   1. prefill_fused_kernel  576 threads: warps 0-15 = two softmax groups (group g owns TMEM buffer S[g] and P buffer g,
 //                            two threads per query row), warp 16 = loaders (K lane, V lane), warp 17 = MMA issuer.
-//        phase A  for every key tile j:      S[j&1] = Q.K_j^T (tcgen05)  ->  fp16 logits written ONCE (coalesced through a
-//                                            shared-memory staging tile); running row max / row sum (online) for the tiles
+//        phase A  for every key tile j:      S[j&1] = Q.K_j^T (tcgen05)  ->  fp16 logits written ONCE (coalesced through
+//                                            warp-private shared-memory staging); running row max / row sum (online) for the tiles
 //                                            the mask leaves alive.  HBM-bound: 32 KiB of logits per tile.
 //        phase B  for every live key tile j: S = Q.K_j^T again (cheaper than re-reading the logits from HBM),
 //                                            p = exp(s - M) / L with the FINAL row statistics -> fp16 P tile in shared memory
@@ -37,12 +37,12 @@ constexpr int kImgBytes = kFT * kFD * 2;       // 32 KiB operand image
 constexpr int kGroupThreads = 256;                // one softmax group: 8 warps, two threads per query row
 constexpr int kLoadWarp = 16, kMmaWarp = 17;
 constexpr int kFusedThreads = 18 * 32;
-constexpr int kStagePitch = kFT * 2 + 16;      // bytes; logits staging row pitch (16-byte stores of 8 rows hit 8 bank groups)
-constexpr int kStageBytes = kFT * kStagePitch; // 34816
+constexpr int kStagePitch = 64 * 2 + 16;       // bytes; a warp stages its 32 rows x 64 logits (16-byte stores of 8 rows hit 8 bank groups)
+constexpr int kStageBytes = 32 * kStagePitch;  // 4608 per warp
 constexpr int kOffQ = 0, kOffK = kImgBytes, kOffV = 3 * kImgBytes, kOffP = 5 * kImgBytes, kOffBars = 7 * kImgBytes;
 constexpr int kOffStats = kOffBars + 256, kOffTmem = kOffStats + 2 * kFT * 8;
 constexpr int kFusedSmem = kOffTmem + 16;
-static_assert(2 * kStageBytes <= 4 * kImgBytes, "phase-A staging must fit in the V ring + P buffers");
+static_assert(16 * kStageBytes + 2048 <= 3 * kImgBytes, "phase-A staging + statistics exchange must fit in the V ring + P[0]");
 static_assert(kFusedSmem <= 232448, "shared memory budget");
 
 enum FusedBar { Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 7, S_FULL = 9, S_EMPTY = 11, P_FULL = 13,
@@ -145,11 +145,12 @@ __global__ void __launch_bounds__(256) mask_classify_kernel(const __half* mask, 
   } else {
     for (int i = 0; i < 8; ++i) v[i] = e0 + i < total ? mask[e0 + i] : __float2half(0.f);
   }
+  const int64_t r = e0 / kv_len;
+  int j = static_cast<int>(e0 - r * kv_len), qi = static_cast<int>(r % q_len);
   for (int i = 0; i < 8 && e0 + i < total; ++i) {
-    const int64_t e = e0 + i;
-    const int j = static_cast<int>(e % kv_len), qi = static_cast<int>((e / kv_len) % q_len);
     const float m = __half2float(v[i]);
     ok = ok && (j <= qi + off ? m == 0.f : m <= -60000.f);
+    if (++j == kv_len) { j = 0; if (++qi == q_len) qi = 0; }
   }
   if (!ok) *flag = 0;
 }
@@ -167,6 +168,7 @@ struct FusedParams {
   int64_t imp_stride;
   int batch, H, n_rep, q_len, kv_len, mt, nt;
   int mode;                 // 1 = causal, 2 = no mask, 0 = mask given: read *mode_flag (1 causal / 0 generic)
+  int debug;                // timing experiments only (tools/microbench.py): 1 = no logit stores, 2 = skip phase B, 4 = no phase-A statistics
   float rs_up;              // nextafter(1/sqrt(D)): fp16(x * rs_up) == fp16(x / sqrt(D)) for every fp16 x (D = 128)
 };
 
@@ -174,6 +176,19 @@ struct FusedParams {
 __device__ __forceinline__ __half2 logit2(float a, float b, float rs_up) {
   const float2 f = __half22float2(__floats2half2_rn(a, b));
   return __floats2half2_rn(f.x * rs_up, f.y * rs_up);
+}
+
+// tcgen05.mma with the two shared-memory descriptors passed as (low, high) words: the high words are compile-time
+// constants and the low words differ from a base by an immediate, so one MMA costs a handful of issue slots
+__device__ __forceinline__ void umma_f16_split(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(static_cast<uint32_t>(accumulate))
+      : "memory");
 }
 
 // additive mask of columns 2i, 2i + 1 of a 32-column chunk; columns past `lim` (beyond kv_len) read as 0
@@ -220,7 +235,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) prefill_fused_kernel(const F
 
   const int last_row = min(m0 + kFT - 1, p.q_len - 1);
   const int nt = p.nt;
-  const int nb = mode == 1 ? min(nt, (last_row + off) / kFT + 1) : nt;      // key tiles the mask leaves alive
+  const int nb = (p.debug & 2) ? 0 : (mode == 1 ? min(nt, (last_row + off) / kFT + 1) : nt);      // key tiles the mask leaves alive
+  const int nb_stats = (p.debug & 4) ? 0 : (mode == 1 ? min(nt, (last_row + off) / kFT + 1) : nt);
 
   if (warp == kLoadWarp) {
     // ===== loaders: contiguous 32 KiB images through the TMA engine; lane 0 feeds Q and the K ring, lane 1 the V ring =====
@@ -238,7 +254,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) prefill_fused_kernel(const F
       }
     } else if (lane == 1) {
       const uint8_t* vimg = p.v_img + kv_img0;
-      mbar_wait_bounded(&bars[A_DONE], 0);                                 // the V ring doubles as phase A's logits staging
+      while (!mbar_try_wait(&bars[A_DONE], 0)) __nanosleep(500);           // the V ring doubles as phase A's logits staging
       for (int j = 0; j < nb; ++j) {
         const int vs = j & 1;
         mbar_wait_bounded(&bars[V_EMPTY + vs], ((j >> 1) & 1) ^ 1);
@@ -249,45 +265,61 @@ __global__ void __launch_bounds__(kFusedThreads, 1) prefill_fused_kernel(const F
     __syncwarp();
   } else if (warp == kMmaWarp) {
     // ===== MMA issuer =====
+    // One lane issues every tcgen05.mma.  The warp shares its scheduler with four softmax warps, so the issue sequence is
+    // kept short: descriptor words are built once (only the 14-bit start-address field changes per MMA) and phase B
+    // issues whichever of "next S tile" / "next P.V" is ready first instead of a fixed order.
     if (lane == 0) {
       constexpr uint32_t idesc_qk = umma_idesc(kFT, kFT, 0);
       constexpr uint32_t idesc_pv = umma_idesc(kFT, kFD, 1);
-      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
+      constexpr uint32_t hi_kmajor = (2048u >> 4) | (1u << 14);            // SBO = 2048, descriptor version 1
+      constexpr uint32_t hi_mnmajor = (128u >> 4) | (1u << 14);            // SBO = 128
+      constexpr uint32_t lbo_kmajor = (128u >> 4) << 16, lbo_mnmajor = (2048u >> 4) << 16;
+      const uint32_t dQ = (smem_u32(sQ) >> 4) | lbo_kmajor, dK = (smem_u32(sK) >> 4) | lbo_kmajor;
+      const uint32_t dP = (smem_u32(sP) >> 4) | lbo_kmajor, dV = (smem_u32(sV) >> 4) | lbo_mnmajor;
       mbar_wait_bounded(&bars[Q_FULL], 0);
       uint32_t jt = 0;                                                     // S tiles issued so far: K slot = S slot = jt & 1
+      auto qk_ready = [&]() {
+        const int s = jt & 1;
+        return mbar_try_wait(&bars[K_FULL + s], (jt >> 1) & 1) && mbar_try_wait(&bars[S_EMPTY + s], ((jt >> 1) & 1) ^ 1);
+      };
       auto issue_qk = [&]() {
         const int s = jt & 1;
-        mbar_wait_bounded(&bars[K_FULL + s], (jt >> 1) & 1);
-        mbar_wait_bounded(&bars[S_EMPTY + s], ((jt >> 1) & 1) ^ 1);
         tc_fence_after();
+        const uint32_t d = tmem + s * kFT, bk = dK + s * (kImgBytes >> 4);
 #pragma unroll
-        for (int ks = 0; ks < kFD / 16; ++ks)
-          umma_f16(tmem + s * kFT, umma_desc(aQ + ks * 256, 128, 2048), umma_desc(aK + s * kImgBytes + ks * 256, 128, 2048),
-                   idesc_qk, ks > 0);
+        for (int ks = 0; ks < kFD / 16; ++ks) umma_f16_split(d, dQ + ks * 16, hi_kmajor, bk + ks * 16, hi_kmajor, idesc_qk, ks > 0);
         umma_commit(&bars[K_EMPTY + s]);
         umma_commit(&bars[S_FULL + s]);
         ++jt;
       };
+      auto pv_ready = [&](int j) {
+        return mbar_try_wait(&bars[P_FULL + ((nt + j) & 1)], (j >> 1) & 1) && mbar_try_wait(&bars[V_FULL + (j & 1)], (j >> 1) & 1);
+      };
       auto issue_pv = [&](int j) {
         const int g = (nt + j) & 1, vs = j & 1;
-        mbar_wait_bounded(&bars[P_FULL + g], (j >> 1) & 1);
-        mbar_wait_bounded(&bars[V_FULL + vs], (j >> 1) & 1);
         tc_fence_after();
+        const uint32_t d = tmem + 2 * kFT, ap = dP + g * (kImgBytes >> 4), bv = dV + vs * (kImgBytes >> 4);
+        if (j == 0) {
 #pragma unroll
-        for (int ks = 0; ks < kFT / 16; ++ks)
-          umma_f16(tmem + 2 * kFT, umma_desc(aP + g * kImgBytes + ks * 256, 128, 2048),
-                   umma_desc(aV + vs * kImgBytes + ks * 4096, 2048, 128), idesc_pv, j > 0 || ks > 0);
+          for (int ks = 0; ks < kFT / 16; ++ks) umma_f16_split(d, ap + ks * 16, hi_kmajor, bv + ks * 256, hi_mnmajor, idesc_pv, ks > 0);
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < kFT / 16; ++ks) umma_f16_split(d, ap + ks * 16, hi_kmajor, bv + ks * 256, hi_mnmajor, idesc_pv, true);
+        }
         umma_commit(&bars[P_EMPTY + g]);
         umma_commit(&bars[V_EMPTY + vs]);
       };
-      for (int j = 0; j < nt; ++j) issue_qk();
-      // phase B: S of tile j + 2 is issued as soon as its group has drained S of tile j into registers, i.e. while that
-      // group is still busy with the exponentials of tile j
-      issue_qk();
-      if (nb > 1) issue_qk();
-      for (int j = 0; j < nb; ++j) {
-        if (j + 2 < nb) issue_qk();
-        issue_pv(j);
+      const long long t0 = clock64();
+      for (int j = 0; j < nt; ++j) {
+        while (!qk_ready()) { if (clock64() - t0 > 4000000000ll) __trap(); }
+        issue_qk();
+      }
+      int qn = 0, pn = 0;                                                  // phase-B S tiles / P.V tiles issued
+      while (pn < nb) {
+        // S of tile qn may run at most two tiles ahead of P.V (its group must have drained S of tile qn - 2: S_EMPTY)
+        if (qn < nb && qk_ready()) { issue_qk(); ++qn; continue; }
+        if (pn < qn && pv_ready(pn)) { issue_pv(pn); ++pn; continue; }
+        if (clock64() - t0 > 4000000000ll) __trap();
       }
       umma_commit(&bars[O_FULL]);
     }
@@ -301,7 +333,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) prefill_fused_kernel(const F
     const uint32_t t_s = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + g * kFT + col0;
     const int row_lim = (mode == 1 ? min(row_g + off, p.kv_len - 1) : p.kv_len - 1);   // last live key of this row
     const __half* mrow = (mode == 0 && row_ok) ? p.mask + (static_cast<int64_t>(b) * p.q_len + row_g) * p.kv_len : nullptr;
-    uint8_t* stage = sV + g * kStageBytes;
+    uint8_t* stage = sV + warp * kStageBytes;                              // warp-private: rows of this TMEM quarter, this column half
     __half* lbase = p.logits + b * p.ls_b + h * p.ls_h;
     const bool vec_ok = (p.ls_q % 8) == 0 && ((reinterpret_cast<uintptr_t>(lbase) & 15) == 0);
     uint32_t suse = 0;
@@ -330,9 +362,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) prefill_fused_kernel(const F
       drain_s();
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        *reinterpret_cast<uint4*>(stage + row * kStagePitch + (col0 + i * 8) * 2) = *reinterpret_cast<const uint4*>(&lg[4 * i]);
+        *reinterpret_cast<uint4*>(stage + lane * kStagePitch + i * 16) = *reinterpret_cast<const uint4*>(&lg[4 * i]);
       const int lim = row_lim - n0 - col0;                                 // columns 0..lim of this thread's 64 are live
-      if (j < nb && row_ok && lim >= 0) {
+      if (j < nb_stats && row_ok && lim >= 0) {
         if (lim >= 63 && mrow == nullptr) {
           __half2 hm = lg[0];
 #pragma unroll
@@ -375,24 +407,25 @@ __global__ void __launch_bounds__(kFusedThreads, 1) prefill_fused_kernel(const F
           }
         }
       }
-      group_sync(1 + g, kGroupThreads);
+      __syncwarp();
       {
-        const int half_w = lane >> 4, piece = lane & 15;                  // 2 rows per warp instruction, 16 pieces of 8 logits
-        const int r0 = wg * 2 + half_w, col = piece * 8;
-        const uint8_t* src = stage + r0 * kStagePitch + col * 2;
-        __half* dst = lbase + static_cast<int64_t>(m0 + r0) * p.ls_q + n0 + col;
-        if (vec_ok && m0 + kFT <= p.q_len && n0 + kFT <= p.kv_len) {
+        // the warp writes its own 32 rows x 128 bytes: 4 rows per instruction, 8 lanes x 16 bytes per row (whole sectors)
+        const int r4 = lane >> 3, piece = lane & 7, col = col0 + piece * 8;
+        const uint8_t* src = stage + r4 * kStagePitch + piece * 16;
+        const int grow0 = m0 + quarter * 32 + r4;
+        __half* dst = lbase + static_cast<int64_t>(grow0) * p.ls_q + n0 + col;
+        if (p.debug & 1) {
+        } else if (vec_ok && m0 + kFT <= p.q_len && n0 + kFT <= p.kv_len) {
 #pragma unroll
-          for (int it = 0; it < kFT / 16; ++it)
-            __stcs(reinterpret_cast<uint4*>(dst + static_cast<int64_t>(it) * 16 * p.ls_q),
-                   *reinterpret_cast<const uint4*>(src + it * 16 * kStagePitch));
+          for (int it = 0; it < 8; ++it)
+            __stcs(reinterpret_cast<uint4*>(dst + static_cast<int64_t>(it) * 4 * p.ls_q),
+                   *reinterpret_cast<const uint4*>(src + it * 4 * kStagePitch));
         } else {
 #pragma unroll 1
-          for (int it = 0; it < kFT / 16; ++it) {
-            const int grow = m0 + r0 + it * 16;
-            if (grow >= p.q_len || n0 + col >= p.kv_len) continue;
-            const uint4 val = *reinterpret_cast<const uint4*>(src + it * 16 * kStagePitch);
-            __half* d = dst + static_cast<int64_t>(it) * 16 * p.ls_q;
+          for (int it = 0; it < 8; ++it) {
+            if (grow0 + it * 4 >= p.q_len || n0 + col >= p.kv_len) continue;
+            const uint4 val = *reinterpret_cast<const uint4*>(src + it * 4 * kStagePitch);
+            __half* d = dst + static_cast<int64_t>(it) * 4 * p.ls_q;
             if (vec_ok && n0 + col + 8 <= p.kv_len) {
               __stcs(reinterpret_cast<uint4*>(d), val);
             } else {
@@ -403,12 +436,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) prefill_fused_kernel(const F
           }
         }
       }
-      group_sync(1 + g, kGroupThreads);
+      __syncwarp();
     }
     // merge the statistics: the two column halves of a row inside the group (through the dead staging tile), then the
     // two groups; the staging region is released to the V loader in between
     {
-      float2* xch = reinterpret_cast<float2*>(stage);
+      float2* xch = reinterpret_cast<float2*>(sV + 16 * kStageBytes + g * 1024);   // past every warp's staging, inside P[0]
       if (half == 1) xch[row] = make_float2(m, l);
       group_sync(1 + g, kGroupThreads);
       if (half == 0) {
@@ -578,6 +611,7 @@ int launch_prefill_fused(const SpattenPrefillArgs* a, cudaStream_t st) {
   p.batch = a->batch; p.H = a->num_heads; p.n_rep = a->num_heads / a->num_kv_heads; p.q_len = a->q_len; p.kv_len = a->kv_len;
   p.mt = mt; p.nt = nt;
   p.mode = a->mask != nullptr ? 0 : ((a->flags & SPATTEN_PREFILL_CAUSAL) ? 1 : 2);
+  p.debug = static_cast<int>((a->flags >> 8) & 7);
   p.rs_up = nextafterf(1.0f / sqrtf(static_cast<float>(kFD)), 1.0f);
   prefill_fused_kernel<<<dim3(mt, a->batch * a->num_heads), kFusedThreads, kFusedSmem, st>>>(p);
   cudaError_t e = cudaGetLastError();

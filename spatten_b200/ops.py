@@ -239,7 +239,7 @@ class DecodeStep:
 
 def prefill_attn(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, kv_len: int, rope: torch.Tensor,
                  q_pos: torch.Tensor, mask: Optional[torch.Tensor] = None, logits: Optional[torch.Tensor] = None,
-                 importance: Optional[torch.Tensor] = None, causal: bool = False, legacy: bool = False):
+                 importance: Optional[torch.Tensor] = None, causal: bool = False, legacy: bool = False, _debug: int = 0):
     """Prefill / chunk attention on the tcgen05 tensor cores -- `spatten_prefill_attn` (head_dim 128).
 
     q fp16 [b,q_len,H,D] un-rotated; the new K/V rows are already in k_cache/v_cache [b,H_kv,cap,D]; kv_len rows
@@ -290,7 +290,7 @@ def prefill_attn(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, 
         _require_cuda(importance)
         a.importance, a.importance_stride = importance.data_ptr(), importance.stride(1)
     a.logits_stride_b, a.logits_stride_h, a.logits_stride_q = logits.stride(0), logits.stride(1), logits.stride(2)
-    a.flags = (_lib.PREFILL_CAUSAL if causal else 0) | (_lib.PREFILL_LEGACY if legacy else 0)
+    a.flags = (_lib.PREFILL_CAUSAL if causal else 0) | (_lib.PREFILL_LEGACY if legacy else 0) | ((_debug & 7) << 8)
     a.scratch_bytes = 0 if legacy else probs.numel()
     if causal and mask is not None:
         raise ValueError("causal=True takes no mask tensor")

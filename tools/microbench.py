@@ -196,9 +196,15 @@ def bench_prefill(iters, sizes=(1024, 4096, 8192)):
         mask = torch.full((S, S), torch.finfo(torch.float16).min, dtype=torch.float16, device=dev).triu(1)[None].contiguous()
         logits = torch.empty((b, H, S, S), dtype=torch.float16, device=dev)
         imp = torch.zeros((b, H, S), dtype=torch.float32, device=dev)
-        for name, kw in (("fused", {}), ("fused+importance", {"importance": imp}), ("fused causal flag", {"causal": True}),
-                         ("three-launch", {"legacy": True})):
-            m = None if kw.get("causal") else mask
+        for name, kw in (("fused", {}), ("fused+importance", {"importance": imp}), ("fused causal flag", {"causal": True}), ("fused no mask", {"nomask": True}),
+                         ("three-launch", {"legacy": True}),
+                         ("dbg: no logit stores", {"causal": True, "_debug": 1}), ("dbg: phase A only", {"causal": True, "_debug": 2}),
+                         ("dbg: phase A only, no stores", {"causal": True, "_debug": 3}), ("dbg: phase A only, no stats", {"causal": True, "_debug": 6}),
+                         ("dbg: phase A only, no stats no stores", {"causal": True, "_debug": 7}), ("dbg: no stats", {"causal": True, "_debug": 4})):
+            if kw.get("_debug") and S < 8192:
+                continue
+            m = None if (kw.get("causal") or kw.get("nomask")) else mask
+            kw = {k: v for k, v in kw.items() if k != "nomask"}
             for _ in range(2):
                 ops.prefill_attn(q, kc, vc, S, rope, pos, m, logits, **kw)
             torch.cuda.synchronize()
