@@ -405,7 +405,9 @@ int spatten_local_v_attn(const SpattenLocalVArgs* args, void* stream);
  * Per (batch, kv head): K and V each stored as an MSB and an LSB 4-bit plane, u8 [tokens, head_dim/2], of the
  * offset-128 int8 code u = clamp(rint(x / scale), -127, 127) + 128 (msb = u >> 4, lsb = u & 15), plus one fp16
  * scale = max|x| / 127 per token (MatrixFetcher.scala:48-51 profiles (4,1)/(8,1); :344-347 MSB left-aligned, LSB
- * right-aligned).  Nibble order inside every 8-dim group: [d0,d2,d4,d6,d1,d3,d5,d7].  Token capacity of every
+ * right-aligned).  Nibble order inside every 8-dim group: [d0,d2,d4,d6,d1,d3,d5,d7]; the sixteen
+ * 8-dim groups of a row are stored in the order [0,1,8,9, 2,3,10,11, 4,5,12,13, 6,7,14,15] (a 16-byte chunk = 16 dims +
+ * their RoPE partners).  Token capacity of every
  * buffer must be a multiple of 8.  head_dim == 128 only. */
 typedef struct SpattenQuantKV {
   void* k_msb; void* k_lsb; void* k_scale;
@@ -438,7 +440,8 @@ typedef struct SpattenQuantDecodeArgs {
   void* logits;             /* optional fp16 [b*H, logits_stride] */
   int64_t logits_stride;
   uint8_t* need_requant;    /* out [b*H]: 1 = row was replayed with the LSB plane */
-  void* workspace;          /* >= spatten_decode_quant_workspace_bytes(...) */
+  void* workspace;          /* >= spatten_decode_quant_workspace_bytes(...), zero-filled ONCE by the caller before first
+                               use (split partials + per-row tickets; the kernel restores the tickets to zero) */
   size_t workspace_bytes;
 } SpattenQuantDecodeArgs;
 size_t spatten_decode_quant_workspace_bytes(int32_t batch, int32_t num_heads, int32_t head_dim);

@@ -280,12 +280,17 @@ def head_prune_mask(cum_head_importance: torch.Tensor, keep_heads: int) -> torch
 
 # nibble position p (bits 4p..4p+3 of each little-endian u32 that covers 8 dims) holds dim _NIB_ORDER[p] of the group
 _NIB_ORDER = [0, 2, 4, 6, 1, 3, 5, 7]
+# word position w of a 128-dim row holds the 8-dim group _WORD_ORDER[w]: every 16-byte chunk kq carries dims
+# [16kq, 16kq+16) followed by their RoPE partners [64+16kq, 64+16kq+16), which is what one lane of the MMA kernel fetches
+_WORD_ORDER = [0, 1, 8, 9, 2, 3, 10, 11, 4, 5, 12, 13, 6, 7, 14, 15]
 
 
 def _pack_nibbles(n: torch.Tensor) -> torch.Tensor:
     """int nibbles [.., D] (dim order) -> u8 [.., D/2] in the plane's fetch order."""
     *lead, D = n.shape
     g = n.reshape(*lead, D // 8, 8)[..., _NIB_ORDER]            # now indexed by nibble position
+    if D == 128:
+        g = g[..., _WORD_ORDER, :]
     return (g[..., 0::2] | (g[..., 1::2] << 4)).reshape(*lead, D // 2).to(torch.uint8)
 
 
@@ -294,6 +299,8 @@ def _unpack_nibbles(p: torch.Tensor) -> torch.Tensor:
     *lead, half = p.shape
     lo, hi = (p & 15).to(torch.int32), (p >> 4).to(torch.int32)
     pos = torch.stack((lo, hi), dim=-1).reshape(*lead, half // 4, 8)       # nibble positions 0..7 of each group
+    if half == 64:
+        pos = pos[..., [_WORD_ORDER.index(c) for c in range(16)], :]
     inv = [_NIB_ORDER.index(d) for d in range(8)]
     return pos[..., inv].reshape(*lead, half * 2)
 
@@ -305,8 +312,9 @@ def quantize_kv_planes(x: torch.Tensor):
     (fp16-rounded), stored as an unsigned byte u = q + 128 split MSB-first into two 4-bit planes:
     msb = u >> 4, lsb = u & 15 (MatrixFetcher.scala:48-51 profiles (4,1)/(8,1); MSB fetch
     left-aligned :344-345, LSB refetch right-aligned :346-347; masked low-4-bit write
-    SpAttenController.scala:230-232).  Nibble order inside every 8-dim group is [d0,d2,d4,d6,d1,d3,d5,d7]
-    (a fetch-friendly interleave, cf. the RTL's bit-reversed layout BMR.scala:59-65).
+    SpAttenController.scala:230-232).  Nibble order inside every 8-dim group is [d0,d2,d4,d6,d1,d3,d5,d7] and
+    the 8-dim groups of a 128-dim row are ordered _WORD_ORDER (a fetch-friendly interleave, cf. the RTL's
+    bit-reversed layout BMR.scala:59-65).
     MSB-only dequant uses the bucket midpoint: x ~ ((msb<<4 | 8) - 128) * scale.
     Self-consistent, not reference-pinned.
     """

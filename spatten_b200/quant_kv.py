@@ -65,7 +65,7 @@ class QuantKVCache:
         need = torch.zeros(b * H, dtype=torch.uint8, device=q.device)
         nbytes = lib.spatten_decode_quant_workspace_bytes(b, H, D)
         if self._ws is None or self._ws.numel() < nbytes:
-            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
+            self._ws = torch.zeros(nbytes, dtype=torch.uint8, device=q.device)      # tickets start at zero; self-resetting
         a = _lib.QuantDecodeArgs()
         a.struct_size = C.sizeof(_lib.QuantDecodeArgs)
         a.batch, a.num_heads, a.num_kv_heads, a.head_dim = b, H, self.num_kv_heads, D
