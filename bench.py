@@ -647,10 +647,52 @@ def run_extras(args, cfg, dev, stream, peak, ms_per_step, timed_graph):
         one_shape("c3_decode_after_cascade", 1, 32, 4096, 24)
         one_shape("c5_per_gpu_shard", 8, 5, 16384, 5)
         others["c4_int4_planes"] = quant_shape(dev, stream, peak, timed_graph, Ls=8)
+        others["c3_prefill_8k"] = prefill_shape(dev, stream)
     except Exception as e:
         others["error"] = f"{type(e).__name__}: {e}"
     ex["other_configs"] = others
     return ex
+
+
+def prefill_shape(dev, stream, S=8192, H=32, D=128):
+    """BASELINE config 3's prefill: one Llama-2-7B layer, S x S causal, every pre-mask logit exported (the reference's
+    `attn_scores`), importance column sums on; the fused tcgen05 kernel next to the three-launch path it replaces."""
+    import torch
+    from spatten_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(11)
+    out = {}
+    with torch.cuda.stream(stream):
+        q = torch.randn((1, S, H, D), generator=g, device=dev, dtype=torch.float16)
+        kc = torch.randn((1, H, S, D), generator=g, device=dev, dtype=torch.float16)
+        vc = torch.randn((1, H, S, D), generator=g, device=dev, dtype=torch.float16)
+        rope = ops.rope_table(D, S, dev)
+        pos = torch.arange(S, device=dev).unsqueeze(0)
+        mask = torch.full((S, S), torch.finfo(torch.float16).min, dtype=torch.float16, device=dev).triu(1)[None].contiguous()
+        logits = torch.empty((1, H, S, S), dtype=torch.float16, device=dev)
+        imp = torch.zeros((1, H, S), dtype=torch.float32, device=dev)
+        for name, kw in (("fused", {"importance": imp}), ("three_launch", {"importance": imp, "legacy": True})):
+            for _ in range(2):
+                ops.prefill_attn(q, kc, vc, S, rope, pos, mask, logits, **kw)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_it = 5 if name == "fused" else 2
+            e0.record(stream)
+            for _ in range(n_it):
+                ops.prefill_attn(q, kc, vc, S, rope, pos, mask, logits, **kw)
+            e1.record(stream)
+            stream.synchronize()
+            out[name + "_ms_per_layer"] = e0.elapsed_time(e1) / n_it
+    ms = out["fused_ms_per_layer"]
+    flops = 4.0 * S * S * H * D
+    sustained = 1435.6
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        sustained = float(json.load(open(p)).get("bf16_tflops_sustained", sustained))
+    out.update({"shape": f"b=1 H={H} S={S} D={D}, additive causal mask tensor (classified on the device), importance on",
+                "dense_equivalent_TFLOPs": flops / ms / 1e9, "frac_of_sustained_tensor_peak": flops / ms / 1e9 / sustained,
+                "logits_GB": H * S * S * 2 / 1e9, "logits_write_GBps": H * S * S * 2 / ms / 1e6,
+                "kernel": "prefill_pack_kernel + mask_classify_kernel + prefill_fused_kernel (tcgen05, one launch for S and P.V)",
+                "prefill_tok_s_attention_core_32_layers": S / (ms * 32 * 1e-3)})
+    return out
 
 
 def quant_shape(dev, stream, peak, timed_graph, Ls=8, b=1, H=32, n=8192, D=128, threshold=0.0):
@@ -681,7 +723,7 @@ def quant_shape(dev, stream, peak, timed_graph, Ls=8, b=1, H=32, n=8192, D=128, 
     return {"us_per_layer": us, "achieved_GBps": by / us / 1e3, "frac": by / us / 1e3 / peak,
             "algorithmic_MiB_per_layer": by / 2**20, "requant_fraction": r,
             "shape": f"b={b} H={H} n={n} D={D}, K int4 MSB (+LSB on replay) + V int4 + fp16 scales",
-            "kernel": "decode_attn_q4_kernel + quant_merge_kernel"}
+            "kernel": "decode_attn_q4_kernel (mma.sync tiles, ticket merge in the same launch)"}
 
 
 def run_quant_config(args, cfg, dev):

@@ -39,14 +39,16 @@ constexpr int kLoadWarp = 16, kMmaWarp = 17;
 constexpr int kFusedThreads = 18 * 32;
 constexpr int kStagePitch = 64 * 2 + 16;       // bytes; a warp stages its 32 rows x 64 logits (16-byte stores of 8 rows hit 8 bank groups)
 constexpr int kStageBytes = 32 * kStagePitch;  // 4608 per warp
-constexpr int kOffQ = 0, kOffK = kImgBytes, kOffV = 3 * kImgBytes, kOffP = 5 * kImgBytes, kOffBars = 7 * kImgBytes;
+// shared memory: [Q slot 0][Q slot 1 (phase A) = P buffer 0 (phase B)][K ring x2][V ring x2 | P buffer 1]; phase A's
+// warp-private logit staging and the statistics exchange live in the (then idle) V ring + P buffer 1
+constexpr int kOffQ = 0, kOffP0 = kImgBytes, kOffK = 2 * kImgBytes, kOffV = 4 * kImgBytes, kOffP1 = 6 * kImgBytes, kOffBars = 7 * kImgBytes;
 constexpr int kOffStats = kOffBars + 256, kOffTmem = kOffStats + 2 * kFT * 8;
 constexpr int kFusedSmem = kOffTmem + 16;
-static_assert(16 * kStageBytes + 2048 <= 3 * kImgBytes, "phase-A staging + statistics exchange must fit in the V ring + P[0]");
+static_assert(16 * kStageBytes + 2048 <= 3 * kImgBytes, "phase-A staging + statistics exchange must fit in the V ring + P buffer 1");
 static_assert(kFusedSmem <= 232448, "shared memory budget");
 
-enum FusedBar { Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 7, S_FULL = 9, S_EMPTY = 11, P_FULL = 13,
-                P_EMPTY = 15, O_FULL = 17, A_DONE = 18, NUM_BARS = 19 };
+enum FusedBar { Q_FULL = 0, Q_EMPTY = 1, K_FULL = 2, K_EMPTY = 4, V_FULL = 6, V_EMPTY = 8, S_FULL = 10, S_EMPTY = 14, P_FULL = 18,
+                P_EMPTY = 20, O_FULL = 22, O_EMPTY = 23, A_DONE = 24, NUM_BARS = 25 };
 
 // byte offset of the 16-byte piece (row r, 8-element chunk c) inside a 128 x 128 fp16 operand image: core matrix
 // (r / 8, c) of 128 contiguous bytes.  As a K-major operand (Q, K, P: rows = M/N, chunks = K) LBO = 128, SBO = 2048;
@@ -202,27 +204,29 @@ __global__ void __launch_bounds__(kFusedThreads, 1) prefill_fused_kernel(const F
   uint8_t* sQ = smem + kOffQ;
   uint8_t* sK = smem + kOffK;
   uint8_t* sV = smem + kOffV;
-  uint8_t* sP = smem + kOffP;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
   float2* sStats = reinterpret_cast<float2*>(smem + kOffStats);
   uint32_t* sTmem = reinterpret_cast<uint32_t*>(smem + kOffTmem);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int mtile = p.mt - 1 - static_cast<int>(blockIdx.x);               // heavy (late) query tiles first
+  // A CTA owns TWO query tiles of one head, the heaviest remaining one and the lightest: every K tile of phase A is
+  // fetched once and multiplied with both (half the L2 -> shared-memory traffic of the logit pass), and under the causal
+  // mask every CTA has the same phase-B work (nb[0] + nb[1] = nt + 1 tiles).
+  const int qt0 = p.mt - 1 - static_cast<int>(blockIdx.x), qt1 = static_cast<int>(blockIdx.x);
+  const bool two = qt1 < qt0;                                              // odd tile count: the middle tile is alone
   const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H, kvh = h / p.n_rep;
-  const int m0 = mtile * kFT;
   const int off = p.kv_len - p.q_len;
 
-  if (warp == kLoadWarp) tmem_alloc(sTmem, 512);                           // S[0], S[1], O: 3 x 128 columns
+  if (warp == kLoadWarp) tmem_alloc(sTmem, 512);                           // phase A: S[2 tiles][2]; phase B: S[0], O, S[2]
   if (tid == kMmaWarp * 32) {
-    mbar_init(&bars[Q_FULL], 1);
+    mbar_init(&bars[Q_FULL], 1); mbar_init(&bars[Q_EMPTY], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars[K_FULL + i], 1);  mbar_init(&bars[K_EMPTY + i], 1);
       mbar_init(&bars[V_FULL + i], 1);  mbar_init(&bars[V_EMPTY + i], 1);
-      mbar_init(&bars[S_FULL + i], 1);  mbar_init(&bars[S_EMPTY + i], kGroupThreads);
       mbar_init(&bars[P_FULL + i], kGroupThreads); mbar_init(&bars[P_EMPTY + i], 1);
     }
-    mbar_init(&bars[O_FULL], 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(&bars[S_FULL + i], 1); mbar_init(&bars[S_EMPTY + i], kGroupThreads); }
+    mbar_init(&bars[O_FULL], 1); mbar_init(&bars[O_EMPTY], 2 * kGroupThreads);
     mbar_init(&bars[A_DONE], 2 * kGroupThreads / 32);
     fence_mbar_init();
   }
@@ -233,10 +237,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) prefill_fused_kernel(const F
   tc_fence_after();
   const uint32_t tmem = *sTmem;
 
-  const int last_row = min(m0 + kFT - 1, p.q_len - 1);
   const int nt = p.nt;
-  const int nb = (p.debug & 2) ? 0 : (mode == 1 ? min(nt, (last_row + off) / kFT + 1) : nt);      // key tiles the mask leaves alive
-  const int nb_stats = (p.debug & 4) ? 0 : (mode == 1 ? min(nt, (last_row + off) / kFT + 1) : nt);
+  // key tiles the mask leaves alive, per query tile
+  auto live_tiles = [&](int qt) { return mode == 1 ? min(nt, (min(qt * kFT + kFT - 1, p.q_len - 1) + off) / kFT + 1) : nt; };
+  const int nl0 = live_tiles(qt0), nl1 = two ? live_tiles(qt1) : 0;
+  const int nb0 = (p.debug & 2) ? 0 : nl0, nb1 = (p.debug & 2) ? 0 : nl1;   // phase-B tiles
+  const int nbt = nb0 + nb1;
 
   if (warp == kLoadWarp) {
     // ===== loaders: contiguous 32 KiB images through the TMA engine; lane 0 feeds Q and the K ring, lane 1 the V ring =====
@@ -244,10 +250,19 @@ __global__ void __launch_bounds__(kFusedThreads, 1) prefill_fused_kernel(const F
     const int64_t kv_img0 = (static_cast<int64_t>(b) * (p.H / p.n_rep) + kvh) * nt * kImgBytes;
     if (lane == 0) {
       const uint8_t* kimg = p.k_img + kv_img0;
-      mbar_expect_tx(&bars[Q_FULL], kImgBytes);
-      bulk_g2s(sQ, p.q_img + (static_cast<int64_t>(bh) * p.mt + mtile) * kImgBytes, kImgBytes, &bars[Q_FULL], policy_evict_first());
-      for (int kuse = 0; kuse < nt + nb; ++kuse) {
-        const int s = kuse & 1, j = kuse < nt ? kuse : kuse - nt;
+      const uint8_t* qimg = p.q_img + static_cast<int64_t>(bh) * p.mt * kImgBytes;
+      const uint64_t once = policy_evict_first();
+      mbar_expect_tx(&bars[Q_FULL], kImgBytes * (two ? 2 : 1));
+      bulk_g2s(sQ, qimg + static_cast<int64_t>(qt0) * kImgBytes, kImgBytes, &bars[Q_FULL], once);
+      if (two) bulk_g2s(sQ + kImgBytes, qimg + static_cast<int64_t>(qt1) * kImgBytes, kImgBytes, &bars[Q_FULL], once);
+      for (int kuse = 0; kuse < nt + nbt; ++kuse) {
+        const int s = kuse & 1;
+        const int j = kuse < nt ? kuse : (kuse - nt < nb0 ? kuse - nt : kuse - nt - nb0);
+        if (kuse == nt + nb0 && nb1 > 0) {                                 // second query tile of phase B: reload it into slot 0
+          mbar_wait_bounded(&bars[Q_EMPTY], 0);
+          mbar_expect_tx(&bars[Q_FULL], kImgBytes);
+          bulk_g2s(sQ, qimg + static_cast<int64_t>(qt1) * kImgBytes, kImgBytes, &bars[Q_FULL], once);
+        }
         mbar_wait_bounded(&bars[K_EMPTY + s], ((kuse >> 1) & 1) ^ 1);
         mbar_expect_tx(&bars[K_FULL + s], kImgBytes);
         bulk_g2s(sK + s * kImgBytes, kimg + static_cast<int64_t>(j) * kImgBytes, kImgBytes, &bars[K_FULL + s], keep);
@@ -255,9 +270,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) prefill_fused_kernel(const F
     } else if (lane == 1) {
       const uint8_t* vimg = p.v_img + kv_img0;
       while (!mbar_try_wait(&bars[A_DONE], 0)) __nanosleep(500);           // the V ring doubles as phase A's logits staging
-      for (int j = 0; j < nb; ++j) {
-        const int vs = j & 1;
-        mbar_wait_bounded(&bars[V_EMPTY + vs], ((j >> 1) & 1) ^ 1);
+      for (int t = 0; t < nbt; ++t) {
+        const int vs = t & 1, j = t < nb0 ? t : t - nb0;
+        mbar_wait_bounded(&bars[V_EMPTY + vs], ((t >> 1) & 1) ^ 1);
         mbar_expect_tx(&bars[V_FULL + vs], kImgBytes);
         bulk_g2s(sV + vs * kImgBytes, vimg + static_cast<int64_t>(j) * kImgBytes, kImgBytes, &bars[V_FULL + vs], keep);
       }
@@ -275,289 +290,330 @@ __global__ void __launch_bounds__(kFusedThreads, 1) prefill_fused_kernel(const F
       constexpr uint32_t hi_mnmajor = (128u >> 4) | (1u << 14);            // SBO = 128
       constexpr uint32_t lbo_kmajor = (128u >> 4) << 16, lbo_mnmajor = (2048u >> 4) << 16;
       const uint32_t dQ = (smem_u32(sQ) >> 4) | lbo_kmajor, dK = (smem_u32(sK) >> 4) | lbo_kmajor;
-      const uint32_t dP = (smem_u32(sP) >> 4) | lbo_kmajor, dV = (smem_u32(sV) >> 4) | lbo_mnmajor;
-      mbar_wait_bounded(&bars[Q_FULL], 0);
-      uint32_t jt = 0;                                                     // S tiles issued so far: K slot = S slot = jt & 1
-      auto qk_ready = [&]() {
-        const int s = jt & 1;
-        return mbar_try_wait(&bars[K_FULL + s], (jt >> 1) & 1) && mbar_try_wait(&bars[S_EMPTY + s], ((jt >> 1) & 1) ^ 1);
-      };
-      auto issue_qk = [&]() {
-        const int s = jt & 1;
-        tc_fence_after();
-        const uint32_t d = tmem + s * kFT, bk = dK + s * (kImgBytes >> 4);
-#pragma unroll
-        for (int ks = 0; ks < kFD / 16; ++ks) umma_f16_split(d, dQ + ks * 16, hi_kmajor, bk + ks * 16, hi_kmajor, idesc_qk, ks > 0);
-        umma_commit(&bars[K_EMPTY + s]);
-        umma_commit(&bars[S_FULL + s]);
-        ++jt;
-      };
-      auto pv_ready = [&](int j) {
-        return mbar_try_wait(&bars[P_FULL + ((nt + j) & 1)], (j >> 1) & 1) && mbar_try_wait(&bars[V_FULL + (j & 1)], (j >> 1) & 1);
-      };
-      auto issue_pv = [&](int j) {
-        const int g = (nt + j) & 1, vs = j & 1;
-        tc_fence_after();
-        const uint32_t d = tmem + 2 * kFT, ap = dP + g * (kImgBytes >> 4), bv = dV + vs * (kImgBytes >> 4);
-        if (j == 0) {
-#pragma unroll
-          for (int ks = 0; ks < kFT / 16; ++ks) umma_f16_split(d, ap + ks * 16, hi_kmajor, bv + ks * 256, hi_mnmajor, idesc_pv, ks > 0);
-        } else {
-#pragma unroll
-          for (int ks = 0; ks < kFT / 16; ++ks) umma_f16_split(d, ap + ks * 16, hi_kmajor, bv + ks * 256, hi_mnmajor, idesc_pv, true);
-        }
-        umma_commit(&bars[P_EMPTY + g]);
-        umma_commit(&bars[V_EMPTY + vs]);
-      };
+      const uint32_t dP0 = (smem_u32(smem + kOffP0) >> 4) | lbo_kmajor, dP1 = (smem_u32(smem + kOffP1) >> 4) | lbo_kmajor;
+      const uint32_t dV = (smem_u32(sV) >> 4) | lbo_mnmajor;
       const long long t0 = clock64();
-      for (int j = 0; j < nt; ++j) {
-        while (!qk_ready()) { if (clock64() - t0 > 4000000000ll) __trap(); }
-        issue_qk();
+      auto spin_guard = [&]() { if (clock64() - t0 > 4000000000ll) __trap(); };
+      mbar_wait_bounded(&bars[Q_FULL], 0);
+      uint32_t kuse = 0;
+      uint32_t sbits = 0;                                                   // bit sb = parity of the next use of S buffer sb
+      auto qk = [&](int qslot, int sb) {                                    // S[sb] = Q[qslot] . K[kuse & 1]^T
+        const int s = kuse & 1;
+        const uint32_t d = tmem + sb * kFT, aq = dQ + qslot * (kImgBytes >> 4), bk = dK + s * (kImgBytes >> 4);
+#pragma unroll
+        for (int ks = 0; ks < kFD / 16; ++ks) umma_f16_split(d, aq + ks * 16, hi_kmajor, bk + ks * 16, hi_kmajor, idesc_qk, ks > 0);
+        umma_commit(&bars[S_FULL + sb]);
+      };
+      // ---- phase A: every K tile against both query tiles ----
+      for (int j = 0; j < nt; ++j, ++kuse) {
+        const int s = kuse & 1, pp = j & 1;
+        mbar_wait_bounded(&bars[K_FULL + s], (kuse >> 1) & 1);
+#pragma unroll 1
+        for (int g = 0; g < (two ? 2 : 1); ++g) {
+          const int sb = g * 2 + pp;
+          mbar_wait_bounded(&bars[S_EMPTY + sb], ((sbits >> sb) & 1) ^ 1);
+          tc_fence_after();
+          qk(g, sb);
+          sbits ^= 1u << sb;
+        }
+        umma_commit(&bars[K_EMPTY + s]);
       }
-      int qn = 0, pn = 0;                                                  // phase-B S tiles / P.V tiles issued
-      while (pn < nb) {
-        // S of tile qn may run at most two tiles ahead of P.V (its group must have drained S of tile qn - 2: S_EMPTY)
-        if (qn < nb && qk_ready()) { issue_qk(); ++qn; continue; }
-        if (pn < qn && pv_ready(pn)) { issue_pv(pn); ++pn; continue; }
-        if (clock64() - t0 > 4000000000ll) __trap();
+      // ---- phase B: one query tile at a time (always in Q slot 0); tile t of the CTA goes to group t & 1 ----
+      int tbase = 0;
+#pragma unroll 1
+      for (int qi = 0; qi < 2; ++qi) {
+        const int nb = qi ? nb1 : nb0;
+        if (nb == 0) continue;
+        if (qi == 1) { mbar_wait_bounded(&bars[Q_FULL], 1); }
+        int qn = 0, pn = 0;
+        while (pn < nb) {
+          if (qn < nb) {                                                    // next S tile: needs its K image and a drained S buffer
+            const int t = tbase + qn, g = t & 1, sb = g * 2, s = kuse & 1;
+            if (mbar_try_wait(&bars[K_FULL + s], (kuse >> 1) & 1) && mbar_try_wait(&bars[S_EMPTY + sb], ((sbits >> sb) & 1) ^ 1)) {
+              tc_fence_after();
+              qk(0, sb);
+              umma_commit(&bars[K_EMPTY + s]);
+              sbits ^= 1u << sb; ++kuse; ++qn;
+              if (qn == nb && qi == 0 && nb1 > 0) umma_commit(&bars[Q_EMPTY]);   // slot 0 may take the second query tile
+              continue;
+            }
+          }
+          if (pn < qn) {                                                    // next P.V: needs the group's P tile and the V image
+            const int t = tbase + pn, g = t & 1, vs = t & 1;
+            if (mbar_try_wait(&bars[P_FULL + g], (t >> 1) & 1) && mbar_try_wait(&bars[V_FULL + vs], (t >> 1) & 1)) {
+              if (pn == 0 && qi == 1 && nb0 > 0) mbar_wait_bounded(&bars[O_EMPTY], 0);   // O of the first tile has been read
+              tc_fence_after();
+              const uint32_t d = tmem + 1 * kFT, ap = g ? dP1 : dP0, bv = dV + vs * (kImgBytes >> 4);
+              if (pn == 0) {
+#pragma unroll
+                for (int ks = 0; ks < kFT / 16; ++ks) umma_f16_split(d, ap + ks * 16, hi_kmajor, bv + ks * 256, hi_mnmajor, idesc_pv, ks > 0);
+              } else {
+#pragma unroll
+                for (int ks = 0; ks < kFT / 16; ++ks) umma_f16_split(d, ap + ks * 16, hi_kmajor, bv + ks * 256, hi_mnmajor, idesc_pv, true);
+              }
+              umma_commit(&bars[P_EMPTY + g]);
+              umma_commit(&bars[V_EMPTY + vs]);
+              ++pn;
+              continue;
+            }
+          }
+          spin_guard();
+        }
+        umma_commit(&bars[O_FULL]);
+        tbase += nb;
       }
-      umma_commit(&bars[O_FULL]);
     }
     __syncwarp();
   } else {
-    // ===== softmax groups: group g drains S[g]; two threads per query row (TMEM lane), 64 key columns each =====
-    const int g = warp >> 3, wg = warp & 7, quarter = warp & 3, half = (warp >> 2) & 1, row = quarter * 32 + lane;
+    // ===== softmax groups: two threads per query row (TMEM lane), 64 key columns each.  Phase A: group g owns query
+    // tile g.  Phase B: the groups alternate key tiles of the current query tile. =====
+    const int g = warp >> 3, quarter = warp & 3, half = (warp >> 2) & 1, row = quarter * 32 + lane;
     const int col0 = half * 64;
-    const int row_g = m0 + row;                                            // query index inside the chunk
-    const bool row_ok = row_g < p.q_len;
-    const uint32_t t_s = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + g * kFT + col0;
-    const int row_lim = (mode == 1 ? min(row_g + off, p.kv_len - 1) : p.kv_len - 1);   // last live key of this row
-    const __half* mrow = (mode == 0 && row_ok) ? p.mask + (static_cast<int64_t>(b) * p.q_len + row_g) * p.kv_len : nullptr;
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
     uint8_t* stage = sV + warp * kStageBytes;                              // warp-private: rows of this TMEM quarter, this column half
     __half* lbase = p.logits + b * p.ls_b + h * p.ls_h;
     const bool vec_ok = (p.ls_q % 8) == 0 && ((reinterpret_cast<uintptr_t>(lbase) & 15) == 0);
-    uint32_t suse = 0;
-    float m = -CUDART_INF_F, l = 0.f;
+    uint32_t sbits = 0;                                                    // bit pp = parity of the next use of this group's S buffer pp
     __half2 lg[32];                                                        // this thread's 64 logits of the current tile
 
-    // S[g] -> fp16 logits in registers, then the buffer goes straight back to the MMA issuer
-    auto drain_s = [&]() {
-      mbar_wait_bounded(&bars[S_FULL + g], suse & 1);
-      ++suse;
+    // S[sb] -> fp16 logits in registers, then the buffer goes straight back to the MMA issuer
+    auto drain_s = [&](int pp) {
+      const int sb = g * 2 + pp;
+      mbar_wait_bounded(&bars[S_FULL + sb], (sbits >> pp) & 1);
+      sbits ^= 1u << pp;
       tc_fence_after();
 #pragma unroll
       for (int c2 = 0; c2 < 2; ++c2) {
         float v[32];
-        tmem_ld32(t_s + c2 * 32, v);
+        tmem_ld32(t_lane + sb * kFT + col0 + c2 * 32, v);
 #pragma unroll
         for (int i = 0; i < 16; ++i) lg[c2 * 16 + i] = logit2(v[2 * i], v[2 * i + 1], p.rs_up);
       }
       tc_fence_before();
-      mbar_arrive(&bars[S_EMPTY + g]);
+      mbar_arrive(&bars[S_EMPTY + sb]);
+    };
+    // per query tile: first row, this thread's row, last live key of the row, mask row
+    auto tile_rows = [&](int qt, int& m0, int& row_g, bool& row_ok, int& row_lim, const __half*& mrow) {
+      m0 = qt * kFT;
+      row_g = m0 + row;
+      row_ok = row_g < p.q_len;
+      row_lim = (mode == 1 ? min(row_g + off, p.kv_len - 1) : p.kv_len - 1);
+      mrow = (mode == 0 && row_ok) ? p.mask + (static_cast<int64_t>(b) * p.q_len + row_g) * p.kv_len : nullptr;
     };
 
-    // ---- phase A: logits + row statistics ----
-    for (int j = g; j < nt; j += 2) {
-      const int n0 = j * kFT;
-      drain_s();
+    // ---- phase A: logits + row statistics of query tile g ----
+    float m = -CUDART_INF_F, l = 0.f;
+    if (g == 0 || two) {
+      int m0, row_g, row_lim; bool row_ok; const __half* mrow;
+      tile_rows(g ? qt1 : qt0, m0, row_g, row_ok, row_lim, mrow);
+      const int nb_stats = (p.debug & 4) ? 0 : (g ? nl1 : nl0);
+      for (int j = 0; j < nt; ++j) {
+        const int n0 = j * kFT;
+        drain_s(j & 1);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        *reinterpret_cast<uint4*>(stage + lane * kStagePitch + i * 16) = *reinterpret_cast<const uint4*>(&lg[4 * i]);
-      const int lim = row_lim - n0 - col0;                                 // columns 0..lim of this thread's 64 are live
-      if (j < nb_stats && row_ok && lim >= 0) {
-        if (lim >= 63 && mrow == nullptr) {
-          __half2 hm = lg[0];
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<uint4*>(stage + lane * kStagePitch + i * 16) = *reinterpret_cast<const uint4*>(&lg[4 * i]);
+        const int lim = row_lim - n0 - col0;                               // columns 0..lim of this thread's 64 are live
+        if (j < nb_stats && row_ok && lim >= 0) {
+          if (lim >= 63 && mrow == nullptr) {
+            __half2 hm = lg[0];
 #pragma unroll
-          for (int i = 1; i < 32; ++i) hm = __hmax2(hm, lg[i]);
-          const float cm = fmaxf(__low2float(hm), __high2float(hm));
-          if (cm > m) { l *= fast_exp2((m - cm) * kLog2e); m = cm; }      // m = -inf: l is 0 and stays 0
-          const float ml2 = m * kLog2e;
-          float part0 = 0.f, part1 = 0.f;
+            for (int i = 1; i < 32; ++i) hm = __hmax2(hm, lg[i]);
+            const float cm = fmaxf(__low2float(hm), __high2float(hm));
+            if (cm > m) { l *= fast_exp2((m - cm) * kLog2e); m = cm; }    // m = -inf: l is 0 and stays 0
+            const float ml2 = m * kLog2e;
+            float part0 = 0.f, part1 = 0.f;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float2 f = __half22float2(lg[i]);
-            part0 += fast_exp2(fmaf(f.x, kLog2e, -ml2));
-            part1 += fast_exp2(fmaf(f.y, kLog2e, -ml2));
-          }
-          l += part0 + part1;
-        } else {
-#pragma unroll
-          for (int cb = 0; cb < 64; cb += 16) {
-            if (cb > lim) break;
-            float x[16];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              __half2 t = lg[(cb >> 1) + i];
-              if (mrow) t = __hadd2_rn(t, mask2(mrow + n0 + col0 + cb, i, lim - cb));   // fp16 add, as attn_weights + attention_mask (:132)
-              const float2 f = __half22float2(t);
-              x[2 * i] = (cb + 2 * i <= lim) ? f.x : -CUDART_INF_F;
-              x[2 * i + 1] = (cb + 2 * i + 1 <= lim) ? f.y : -CUDART_INF_F;
+            for (int i = 0; i < 32; ++i) {
+              const float2 f = __half22float2(lg[i]);
+              part0 += fast_exp2(fmaf(f.x, kLog2e, -ml2));
+              part1 += fast_exp2(fmaf(f.y, kLog2e, -ml2));
             }
-            float cm = x[0];
+            l += part0 + part1;
+          } else {
 #pragma unroll
-            for (int i = 1; i < 16; ++i) cm = fmaxf(cm, x[i]);
-            if (cm > m) { l *= fast_exp2((m - cm) * kLog2e); m = cm; }
-            if (m > -CUDART_INF_F) {
-              const float ml2 = m * kLog2e;
-              float part = 0.f;
+            for (int cb = 0; cb < 64; cb += 16) {
+              if (cb > lim) break;
+              float x[16];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) part += fast_exp2(fmaf(x[i], kLog2e, -ml2));
-              l += part;
+              for (int i = 0; i < 8; ++i) {
+                __half2 t = lg[(cb >> 1) + i];
+                if (mrow) t = __hadd2_rn(t, mask2(mrow + n0 + col0 + cb, i, lim - cb));   // fp16 add, as attn_weights + attention_mask (:132)
+                const float2 f = __half22float2(t);
+                x[2 * i] = (cb + 2 * i <= lim) ? f.x : -CUDART_INF_F;
+                x[2 * i + 1] = (cb + 2 * i + 1 <= lim) ? f.y : -CUDART_INF_F;
+              }
+              float cm = x[0];
+#pragma unroll
+              for (int i = 1; i < 16; ++i) cm = fmaxf(cm, x[i]);
+              if (cm > m) { l *= fast_exp2((m - cm) * kLog2e); m = cm; }
+              if (m > -CUDART_INF_F) {
+                const float ml2 = m * kLog2e;
+                float part = 0.f;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) part += fast_exp2(fmaf(x[i], kLog2e, -ml2));
+                l += part;
+              }
             }
           }
         }
-      }
-      __syncwarp();
-      {
-        // the warp writes its own 32 rows x 128 bytes: 4 rows per instruction, 8 lanes x 16 bytes per row (whole sectors)
-        const int r4 = lane >> 3, piece = lane & 7, col = col0 + piece * 8;
-        const uint8_t* src = stage + r4 * kStagePitch + piece * 16;
-        const int grow0 = m0 + quarter * 32 + r4;
-        __half* dst = lbase + static_cast<int64_t>(grow0) * p.ls_q + n0 + col;
-        if (p.debug & 1) {
-        } else if (vec_ok && m0 + kFT <= p.q_len && n0 + kFT <= p.kv_len) {
+        __syncwarp();
+        {
+          // the warp writes its own 32 rows x 128 bytes: 4 rows per instruction, 8 lanes x 16 bytes per row (whole sectors)
+          const int r4 = lane >> 3, piece = lane & 7, col = col0 + piece * 8;
+          const uint8_t* src = stage + r4 * kStagePitch + piece * 16;
+          const int grow0 = m0 + quarter * 32 + r4;
+          __half* dst = lbase + static_cast<int64_t>(grow0) * p.ls_q + n0 + col;
+          if (p.debug & 1) {
+          } else if (vec_ok && m0 + kFT <= p.q_len && n0 + kFT <= p.kv_len) {
 #pragma unroll
-          for (int it = 0; it < 8; ++it)
-            __stcs(reinterpret_cast<uint4*>(dst + static_cast<int64_t>(it) * 4 * p.ls_q),
-                   *reinterpret_cast<const uint4*>(src + it * 4 * kStagePitch));
-        } else {
+            for (int it = 0; it < 8; ++it)
+              __stcs(reinterpret_cast<uint4*>(dst + static_cast<int64_t>(it) * 4 * p.ls_q),
+                     *reinterpret_cast<const uint4*>(src + it * 4 * kStagePitch));
+          } else {
 #pragma unroll 1
-          for (int it = 0; it < 8; ++it) {
-            if (grow0 + it * 4 >= p.q_len || n0 + col >= p.kv_len) continue;
-            const uint4 val = *reinterpret_cast<const uint4*>(src + it * 4 * kStagePitch);
-            __half* d = dst + static_cast<int64_t>(it) * 4 * p.ls_q;
-            if (vec_ok && n0 + col + 8 <= p.kv_len) {
-              __stcs(reinterpret_cast<uint4*>(d), val);
-            } else {
-              const __half* hv = reinterpret_cast<const __half*>(&val);
-              for (int i = 0; i < 8; ++i)
-                if (n0 + col + i < p.kv_len) d[i] = hv[i];
+            for (int it = 0; it < 8; ++it) {
+              if (grow0 + it * 4 >= p.q_len || n0 + col >= p.kv_len) continue;
+              const uint4 val = *reinterpret_cast<const uint4*>(src + it * 4 * kStagePitch);
+              __half* d = dst + static_cast<int64_t>(it) * 4 * p.ls_q;
+              if (vec_ok && n0 + col + 8 <= p.kv_len) {
+                __stcs(reinterpret_cast<uint4*>(d), val);
+              } else {
+                const __half* hv = reinterpret_cast<const __half*>(&val);
+                for (int i = 0; i < 8; ++i)
+                  if (n0 + col + i < p.kv_len) d[i] = hv[i];
+              }
             }
           }
         }
+        __syncwarp();
       }
-      __syncwarp();
     }
-    // merge the statistics: the two column halves of a row inside the group (through the dead staging tile), then the
-    // two groups; the staging region is released to the V loader in between
+    // merge the two column halves of every row (through shared memory past the staging tiles) and publish the tile's
+    // statistics; the staging region is released to the V loader
     {
-      float2* xch = reinterpret_cast<float2*>(sV + 16 * kStageBytes + g * 1024);   // past every warp's staging, inside P[0]
+      float2* xch = reinterpret_cast<float2*>(sV + 16 * kStageBytes + g * 1024);
       if (half == 1) xch[row] = make_float2(m, l);
       group_sync(1 + g, kGroupThreads);
       if (half == 0) {
         const float2 o2 = xch[row];
         const float M = fmaxf(m, o2.x);
         if (M > -CUDART_INF_F) { l = l * fast_exp2((m - M) * kLog2e) + o2.y * fast_exp2((o2.x - M) * kLog2e); m = M; }
+        else { m = 0.f; l = 1.f; }                                         // fully masked row (generic mask only)
         sStats[g * kFT + row] = make_float2(m, l);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[A_DONE]);
       group_sync(3, 2 * kGroupThreads);
-      const float2 s0 = sStats[row], s1 = sStats[kFT + row];
-      const float M = fmaxf(s0.x, s1.x);
-      if (M > -CUDART_INF_F) {
-        l = s0.y * fast_exp2((s0.x - M) * kLog2e) + s1.y * fast_exp2((s1.x - M) * kLog2e);
-        m = M;
-      } else {
-        m = 0.f; l = 1.f;                                                  // fully masked row (generic mask only)
-      }
     }
-    // p = exp2(x * log2e - sub): 1 / L folded into the exponent; padding rows get p = 0 (nothing for the column sums)
-    const float sub_l2 = row_ok ? fmaf(m, kLog2e, __log2f(l)) : CUDART_INF_F;
 
-    // ---- phase B: P = exp(S - M) / L -> shared memory -> O += P.V, column sums ----
-    uint8_t* pimg = sP + g * kImgBytes;
+    // ---- phase B: P = exp(S - M) / L -> shared memory -> O += P.V, column sums; then O -> out ----
+    uint8_t* pimg = smem + (g ? kOffP1 : kOffP0);
     float* imp = p.importance ? p.importance + (static_cast<int64_t>(b) * p.H + h) * p.imp_stride : nullptr;
-    uint32_t puse = 0;
-    for (int j = (g + nt) & 1; j < nb; j += 2, ++puse) {
-      const int n0 = j * kFT;
-      drain_s();
-      const int lim = row_lim - n0 - col0;
-      if (lim >= 63 && mrow == nullptr) {
+    int tbase = 0;
+#pragma unroll 1
+    for (int qi = 0; qi < 2; ++qi) {
+      const int nb = qi ? nb1 : nb0;
+      if (nb == 0) continue;
+      int m0, row_g, row_lim; bool row_ok; const __half* mrow;
+      tile_rows(qi ? qt1 : qt0, m0, row_g, row_ok, row_lim, mrow);
+      const float2 st = sStats[qi * kFT + row];
+      // p = exp2(x * log2e - sub): 1 / L folded into the exponent; padding rows get p = 0 (nothing for the column sums)
+      const float sub_l2 = row_ok ? fmaf(st.x, kLog2e, __log2f(st.y)) : CUDART_INF_F;
+#pragma unroll 1
+      for (int t = tbase + ((tbase ^ g) & 1); t < tbase + nb; t += 2) {     // this group's tiles: t & 1 == g
+        const int n0 = (t - tbase) * kFT;
+        drain_s(0);
+        const int lim = row_lim - n0 - col0;
+        if (lim >= 63 && mrow == nullptr) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float2 f = __half22float2(lg[i]);
-          lg[i] = __floats2half2_rn(fast_exp2(fmaf(f.x, kLog2e, -sub_l2)), fast_exp2(fmaf(f.y, kLog2e, -sub_l2)));
+          for (int i = 0; i < 32; ++i) {
+            const float2 f = __half22float2(lg[i]);
+            lg[i] = __floats2half2_rn(fast_exp2(fmaf(f.x, kLog2e, -sub_l2)), fast_exp2(fmaf(f.y, kLog2e, -sub_l2)));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            __half2 tt = lg[i];
+            if (mrow) tt = __hadd2_rn(tt, mask2(mrow + n0 + col0, i, lim));
+            const float2 f = __half22float2(tt);
+            const float p0 = 2 * i <= lim ? fast_exp2(fmaf(f.x, kLog2e, -sub_l2)) : 0.f;
+            const float p1 = 2 * i + 1 <= lim ? fast_exp2(fmaf(f.y, kLog2e, -sub_l2)) : 0.f;
+            lg[i] = __floats2half2_rn(p0, p1);
+          }
         }
-      } else {
+        mbar_wait_bounded(&bars[P_EMPTY + g], ((t >> 1) & 1) ^ 1);         // P.V of this group's previous tile has read the buffer
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          __half2 t = lg[i];
-          if (mrow) t = __hadd2_rn(t, mask2(mrow + n0 + col0, i, lim));
-          const float2 f = __half22float2(t);
-          const float p0 = 2 * i <= lim ? fast_exp2(fmaf(f.x, kLog2e, -sub_l2)) : 0.f;
-          const float p1 = 2 * i + 1 <= lim ? fast_exp2(fmaf(f.y, kLog2e, -sub_l2)) : 0.f;
-          lg[i] = __floats2half2_rn(p0, p1);
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<uint4*>(pimg + img_off(row, half * 8 + i)) = *reinterpret_cast<const uint4*>(&lg[4 * i]);
+        fence_proxy_async();                                               // generic-proxy writes -> visible to the tensor core
+        mbar_arrive(&bars[P_FULL + g]);
+        if (imp) {
+          group_sync(1 + g, kGroupThreads);
+          // column sums of the tile just written: thread (chunk c, part hp, sub) adds rows sub + 8i, i in [8hp, 8hp + 8), of
+          // the 8 columns of chunk c; the 8 x 2 lanes that share a chunk then reduce-scatter
+          const int tg = (warp & 7) * 32 + lane, c = tg >> 4, hp = (tg >> 3) & 1, sub = tg & 7;
+          float acc[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+          const __half2 one = __floats2half2_rn(1.f, 1.f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint4 x = *reinterpret_cast<const uint4*>(pimg + (hp * 8 + i) * 2048 + c * 128 + sub * 16);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&x);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              acc[2 * e] = fhfma_lo(h2[e], one, acc[2 * e]);
+              acc[2 * e + 1] = fhfma_hi(h2[e], one, acc[2 * e + 1]);
+            }
+          }
+          float a4[4], a2[2];
+          {
+            const bool hi = sub & 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float send = hi ? acc[i] : acc[i + 4];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+              a4[i] = (hi ? acc[i + 4] : acc[i]) + recv;
+            }
+          }
+          {
+            const bool hi = sub & 2;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float send = hi ? a4[i] : a4[i + 2];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+              a2[i] = (hi ? a4[i + 2] : a4[i]) + recv;
+            }
+          }
+          const bool hi1 = sub & 1;
+          const float send = hi1 ? a2[0] : a2[1];
+          const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+          float total = (hi1 ? a2[1] : a2[0]) + recv;                      // column c*8 + sub over this lane's 64 rows
+          total += __shfl_xor_sync(0xffffffffu, total, 8);                 // + the other 64 rows
+          const int col = n0 + c * 8 + sub;
+          if (hp == 0 && col < p.kv_len && total != 0.f) atomicAdd(imp + col, total);
+          group_sync(1 + g, kGroupThreads);                                // nobody overwrites P[g] while a neighbour still sums it
         }
       }
-      mbar_wait_bounded(&bars[P_EMPTY + g], (puse & 1) ^ 1);               // P.V of this group's previous tile has read the buffer
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        *reinterpret_cast<uint4*>(pimg + img_off(row, half * 8 + i)) = *reinterpret_cast<const uint4*>(&lg[4 * i]);
-      fence_proxy_async();                                                 // generic-proxy writes -> visible to the tensor core
-      mbar_arrive(&bars[P_FULL + g]);
-      if (imp) {
-        group_sync(1 + g, kGroupThreads);
-        // column sums of the tile just written: thread (chunk c, part hp, sub) adds rows sub + 8i, i in [8hp, 8hp + 8), of
-        // the 8 columns of chunk c; the 8 x 2 lanes that share a chunk then reduce-scatter
-        const int tg = wg * 32 + lane, c = tg >> 4, hp = (tg >> 3) & 1, sub = tg & 7;
-        float acc[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-        const __half2 one = __floats2half2_rn(1.f, 1.f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint4 x = *reinterpret_cast<const uint4*>(pimg + (hp * 8 + i) * 2048 + c * 128 + sub * 16);
-          const __half2* h2 = reinterpret_cast<const __half2*>(&x);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            acc[2 * e] = fhfma_lo(h2[e], one, acc[2 * e]);
-            acc[2 * e + 1] = fhfma_hi(h2[e], one, acc[2 * e + 1]);
-          }
-        }
-        float a4[4], a2[2];
-        {
-          const bool hi = sub & 4;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float send = hi ? acc[i] : acc[i + 4];
-            const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
-            a4[i] = (hi ? acc[i + 4] : acc[i]) + recv;
-          }
-        }
-        {
-          const bool hi = sub & 2;
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const float send = hi ? a4[i] : a4[i + 2];
-            const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
-            a2[i] = (hi ? a4[i + 2] : a4[i]) + recv;
-          }
-        }
-        const bool hi1 = sub & 1;
-        const float send = hi1 ? a2[0] : a2[1];
-        const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-        float total = (hi1 ? a2[1] : a2[0]) + recv;                        // column c*8 + sub over this lane's 64 rows
-        total += __shfl_xor_sync(0xffffffffu, total, 8);                   // + the other 64 rows
-        const int col = n0 + c * 8 + sub;
-        if (hp == 0 && col < p.kv_len && total != 0.f) atomicAdd(imp + col, total);
-        group_sync(1 + g, kGroupThreads);                                  // nobody overwrites P[g] while a neighbour still sums it
-      }
-    }
+      tbase += nb;
 
-    // ---- O: TMEM -> fp16 -> out[b, q, h, :]; thread (group g, half) writes head_dim columns [32(2g + half), +32) ----
-    mbar_wait_bounded(&bars[O_FULL], 0);
-    tc_fence_after();
-    const int oc = (g * 2 + half) * 32;
-    float v[32];
-    tmem_ld32(tmem + (static_cast<uint32_t>(quarter * 32) << 16) + 2 * kFT + oc, v);
-    if (row_ok) {
-      __half* dst = p.out + ((static_cast<int64_t>(b) * p.q_len + row_g) * p.H + h) * kFD + oc;
-      __align__(16) __half2 o[16];
+      // O: TMEM -> fp16 -> out[b, q, h, :]; thread (group g, half) writes head_dim columns [32(2g + half), +32)
+      mbar_wait_bounded(&bars[O_FULL], (qi == 1 && nb0 > 0) ? 1 : 0);
+      tc_fence_after();
+      const int oc = (g * 2 + half) * 32;
+      float v[32];
+      tmem_ld32(t_lane + 1 * kFT + oc, v);
+      tc_fence_before();
+      mbar_arrive(&bars[O_EMPTY]);
+      if (row_ok) {
+        __half* dst = p.out + ((static_cast<int64_t>(b) * p.q_len + row_g) * p.H + h) * kFD + oc;
+        __align__(16) __half2 o[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) o[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        for (int i = 0; i < 16; ++i) o[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(o)[i];
+        for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(o)[i];
+      }
     }
   }
   tc_fence_before();
@@ -613,7 +669,7 @@ int launch_prefill_fused(const SpattenPrefillArgs* a, cudaStream_t st) {
   p.mode = a->mask != nullptr ? 0 : ((a->flags & SPATTEN_PREFILL_CAUSAL) ? 1 : 2);
   p.debug = static_cast<int>((a->flags >> 8) & 7);
   p.rs_up = nextafterf(1.0f / sqrtf(static_cast<float>(kFD)), 1.0f);
-  prefill_fused_kernel<<<dim3(mt, a->batch * a->num_heads), kFusedThreads, kFusedSmem, st>>>(p);
+  prefill_fused_kernel<<<dim3((mt + 1) / 2, a->batch * a->num_heads), kFusedThreads, kFusedSmem, st>>>(p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? SPATTEN_OK : cuda_fail(e, "spatten_prefill_attn (fused) launch");
 }

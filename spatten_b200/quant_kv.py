@@ -62,7 +62,7 @@ class QuantKVCache:
         _require_cuda(q, rope, q_pos, logits)
         b, H, D = q.shape
         out = torch.empty_like(q)
-        need = torch.zeros(b * H, dtype=torch.uint8, device=q.device)
+        need = torch.empty(b * H, dtype=torch.uint8, device=q.device)      # pass 1 writes every row's decision
         nbytes = lib.spatten_decode_quant_workspace_bytes(b, H, D)
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = torch.zeros(nbytes, dtype=torch.uint8, device=q.device)      # tickets start at zero; self-resetting
