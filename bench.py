@@ -513,8 +513,10 @@ def run_ours(args):
             "roofline": roofline, "modes": modes, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": launches * args.steps, "cuda_graph": graphed,
             "collective": None if world == 1 else (
-                f"fused: spatten_decode_step stores every finished [D={D}] row into all {world} peers' gather buffers over "
-                f"NVLink (whole-warp 8-byte stores) + one release per (row, peer) flag; [b={b}, H/N={Hl}] rows per layer"),
+                f"fused: spatten_decode_step writes every finished [D={D}] row into the local slot of a symmetric gather buffer; "
+                f"the merge warp of one designated CTA per layer copies the finished layer ([b={b}, H/N={Hl}] rows) into the "
+                f"{world - 1} peers' buffers over NVLink and releases one system-scope flag per peer; the launch ends when every "
+                f"peer's flags of every layer have arrived (no NCCL call in the data path)"),
             "exchange_parity": exchange_parity,
             "peer_wait_timed_out": None if world == 1 else any(s.timed_out() for s in steps_by_mode.values()),
             "pdl": bool(head_mode == "per_layer" and not args.no_pdl),

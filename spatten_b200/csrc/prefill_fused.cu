@@ -134,25 +134,33 @@ __global__ void __launch_bounds__(128) prefill_pack_kernel(const PackParams p) {
 }
 
 // *flag = 0 unless mask[b, i, j] is 0 for j <= i + (kv_len - q_len) and <= -60000 (or -inf) beyond: the standard additive
-// causal mask (HF `_make_causal_mask` fills with finfo.min = -65504).  A thread checks 8 consecutive elements.
+// causal mask (HF `_make_causal_mask` fills with finfo.min = -65504).  A thread checks 8 consecutive elements; chunks that
+// lie wholly on one side of the diagonal are tested on the raw bit patterns (two packed compares per 4 bytes), so the
+// kernel runs at memory speed.
 __global__ void __launch_bounds__(256) mask_classify_kernel(const __half* mask, int64_t total, int q_len, int kv_len, int* flag) {
   const int64_t e0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   if (e0 >= total) return;
   const int off = kv_len - q_len;
-  bool ok = true;
-  const bool vec = e0 + 8 <= total && (reinterpret_cast<uintptr_t>(mask + e0) & 15) == 0;
-  __align__(16) __half v[8];
-  if (vec) {
-    *reinterpret_cast<uint4*>(v) = __ldg(reinterpret_cast<const uint4*>(mask + e0));
-  } else {
-    for (int i = 0; i < 8; ++i) v[i] = e0 + i < total ? mask[e0 + i] : __float2half(0.f);
-  }
   const int64_t r = e0 / kv_len;
   int j = static_cast<int>(e0 - r * kv_len), qi = static_cast<int>(r % q_len);
-  for (int i = 0; i < 8 && e0 + i < total; ++i) {
-    const float m = __half2float(v[i]);
-    ok = ok && (j <= qi + off ? m == 0.f : m <= -60000.f);
-    if (++j == kv_len) { j = 0; if (++qi == q_len) qi = 0; }
+  bool ok = true;
+  const bool vec = e0 + 8 <= total && (reinterpret_cast<uintptr_t>(mask + e0) & 15) == 0;
+  if (vec && j + 8 <= kv_len && (j + 7 <= qi + off || j > qi + off)) {
+    const uint4 v = __ldcs(reinterpret_cast<const uint4*>(mask + e0));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    if (j + 7 <= qi + off) {                                    // visible: +0 or -0
+      ok = (((w[0] | w[1] | w[2] | w[3]) & 0x7fff7fffu) == 0);
+    } else {                                                    // masked: fp16 bits in [0xFB53 (-60000), 0xFC00 (-inf)]
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        ok = ok && (__vcmpgeu2(w[i], 0xFB53FB53u) & __vcmpleu2(w[i], 0xFC00FC00u)) == 0xffffffffu;
+    }
+  } else {
+    for (int i = 0; i < 8 && e0 + i < total; ++i) {
+      const float m = __half2float(mask[e0 + i]);
+      ok = ok && (j <= qi + off ? m == 0.f : m <= -60000.f);
+      if (++j == kv_len) { j = 0; if (++qi == q_len) qi = 0; }
+    }
   }
   if (!ok) *flag = 0;
 }
