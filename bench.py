@@ -547,8 +547,8 @@ def run_extras(args, cfg, dev, stream, peak, ms_per_step, timed_graph):
     S = cfg["seq"]
     with torch.cuda.stream(stream):
         pk = [(torch.randn((1, H, S, D), generator=g, device=dev, dtype=torch.float16),
-               torch.randn((1, H, S, D), generator=g, device=dev, dtype=torch.float16)) for _ in range(4)]
-        sc = [torch.randn((1, H, 1, S), generator=g, device=dev, dtype=torch.float16) for _ in range(4)]
+               torch.randn((1, H, S, D), generator=g, device=dev, dtype=torch.float16)) for _ in range(L)]
+        sc = [torch.randn((1, H, 1, S), generator=g, device=dev, dtype=torch.float16) for _ in range(L)]
         with contextlib.redirect_stdout(io.StringIO()):
             cache = SpAttenKVCache(cfg["start"], cfg["recent"], cfg["important"])
         cache.apply_token_pruning(pk, 0, sc)
@@ -557,9 +557,9 @@ def run_extras(args, cfg, dev, stream, peak, ms_per_step, timed_graph):
         for _ in range(5):
             cache.apply_token_pruning(pk, 0, sc)
         torch.cuda.synchronize()
-        per_layer_ms = (time.perf_counter() - t0) * 1e3 / 20
+        per_layer_ms = (time.perf_counter() - t0) * 1e3 / (5 * L)      # the whole model's cache per call: two launches
     keep_total = cfg["start"] + cfg["important"] + cfg["recent"]
-    ex["prune"] = {"ms_per_layer": per_layer_ms, "shape": f"{S} -> {keep_total} tokens, {H} heads",
+    ex["prune"] = {"ms_per_layer": per_layer_ms, "shape": f"{S} -> {keep_total} tokens, {H} heads, {L} layers per call (wall clock incl. host)",
                    "gather_GBps": 4 * H * keep_total * D * 2 / (per_layer_ms * 1e-3) / 1e9,
                    "tok_s_incl_prune_every_64_tokens": 64.0 / (64 * ms_per_step * 1e-3 + per_layer_ms * L * 1e-3)}
     del pk, sc

@@ -198,7 +198,8 @@ struct GatherParams {
 // grid.x = batch * heads * 2 (K then V); grid.y = row tiles (out of place) or 1 (in place: tiles are walked in
 // ascending order by one CTA, which is safe because keep[] is strictly ascending so dst row <= src row and a
 // tile's sources are read into registers before any of its destinations are written).
-__global__ void __launch_bounds__(kGatherThreads) kv_gather_kernel(const GatherParams p) {
+template <int kMaxPer>    // 16-byte chunks per thread per 64-row tile: 4 covers rows of <= 256 bytes (fp16 head_dim 128) at half the registers
+__global__ void __launch_bounds__(kGatherThreads, kMaxPer <= 4 ? 6 : 3) kv_gather_kernel(const GatherParams p) {
   const int which = blockIdx.x & 1;
   const int bh = blockIdx.x >> 1;
   const int h = bh % p.num_heads, b = bh / p.num_heads;
@@ -216,7 +217,6 @@ __global__ void __launch_bounds__(kGatherThreads) kv_gather_kernel(const GatherP
   const int cpr = p.row_bytes >> 4;                       // 16-byte chunks per row
   const int chunks = kGatherTileRows * cpr;
   const int n_tiles = (p.keep_total + kGatherTileRows - 1) / kGatherTileRows;
-  constexpr int kMaxPer = 8;                              // chunks per thread per tile (row_bytes <= 512)
   for (int t = p.in_place ? 0 : blockIdx.y; t < n_tiles; t += p.in_place ? 1 : gridDim.y) {
     uint4 v[kMaxPer];
     int drow[kMaxPer];
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(kGatherThreads) kv_gather_kernel(const GatherP
           const int srow = keep[r];
           if (!(p.in_place && srow == r)) {
             drow[i] = r;
-            v[i] = *reinterpret_cast<const uint4*>(src + static_cast<int64_t>(srow) * p.row_bytes + (ch % cpr) * 16);
+            v[i] = __ldcs(reinterpret_cast<const uint4*>(src + static_cast<int64_t>(srow) * p.row_bytes + (ch % cpr) * 16));   // read once
           }
         }
       }
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(kGatherThreads) kv_gather_kernel(const GatherP
     for (int i = 0; i < kMaxPer; ++i) {
       const int ch = threadIdx.x + i * kGatherThreads;
       if (drow[i] >= 0)
-        *reinterpret_cast<uint4*>(dst + static_cast<int64_t>(drow[i]) * p.row_bytes + (ch % cpr) * 16) = v[i];
+        __stcs(reinterpret_cast<uint4*>(dst + static_cast<int64_t>(drow[i]) * p.row_bytes + (ch % cpr) * 16), v[i]);
     }
     if (p.in_place) __syncthreads();
   }
@@ -323,7 +323,8 @@ extern "C" int spatten_kv_gather(const SpattenGatherArgs* a, void* stream) {
   p.num_heads = a->num_heads; p.keep_total = a->keep_total; p.row_bytes = a->row_bytes; p.in_place = ipk ? 1 : 0;
   const int n_tiles = (a->keep_total + kGatherTileRows - 1) / kGatherTileRows;
   dim3 grid(a->batch * a->num_heads * 2, ipk ? 1 : std::min(n_tiles, 64));
-  kv_gather_kernel<<<grid, kGatherThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  if (a->row_bytes <= 256) kv_gather_kernel<4><<<grid, kGatherThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  else kv_gather_kernel<8><<<grid, kGatherThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? SPATTEN_OK : cuda_fail(e, "kv_gather_kernel launch");
 }
@@ -363,7 +364,8 @@ extern "C" int spatten_prune_layers(const SpattenPruneLayersArgs* a, void* strea
   gp.layers = a->layers;
   const int n_tiles = (keep_total + kGatherTileRows - 1) / kGatherTileRows;
   dim3 grid(a->batch * a->num_heads * 2, std::min(n_tiles, 64), a->num_layers);
-  kv_gather_kernel<<<grid, kGatherThreads, 0, st>>>(gp);
+  if (gp.row_bytes <= 256) kv_gather_kernel<4><<<grid, kGatherThreads, 0, st>>>(gp);
+  else kv_gather_kernel<8><<<grid, kGatherThreads, 0, st>>>(gp);
   e = cudaGetLastError();
   return e == cudaSuccess ? SPATTEN_OK : cuda_fail(e, "kv_gather_kernel launch");
 }
