@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(kQThreads, 1) decode_attn_q4_kernel(const Quan
   const int bi = row_ok ? row / p.H : 0, h = row_ok ? row % p.H : 0, kvh = h / p.n_rep;
   const bool live = row_ok && (!LSB || p.need[row] != 0);      // pass 2 replays only the rows flagged by the requant decision
   const int my_tiles = live ? (ntiles - sub + p.spc - 1) / p.spc : 0;       // tiles sub, sub + spc, ...
+  if (!__syncthreads_or(live ? 1 : 0)) return;                 // pass 2: none of this CTA's rows is replayed
 
   const int64_t poff = bi * p.kv.plane_stride_b + kvh * p.kv.plane_stride_h;
   const int64_t soff = bi * p.kv.scale_stride_b + kvh * p.kv.scale_stride_h;
