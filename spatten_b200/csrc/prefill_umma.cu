@@ -1,4 +1,7 @@
-// Prefill attention on the 5th-generation tensor cores -- spatten_prefill_attn().
+// Prefill attention on the 5th-generation tensor cores -- spatten_prefill_attn(): the entry point and the THREE-LAUNCH path.
+// The default path is the single fused kernel in prefill_fused.cu (taken whenever the caller's scratch is large enough for
+// the operand images); the kernels below are the round-1 structure, kept as the fallback (SPATTEN_PREFILL_LEGACY, scratch_bytes
+// == 0) and as the in-tree cross-check of the fused kernel (tests/test_prefill_umma_gpu.py).
 //
 // Replaces llama_pos_shift_attention_forward for q_len > 1 (reference spatten_llm/pos_shift/modify_llama.py:86-144)
 // with the reference's own three-step structure, because the reference *exports* the full pre-mask logit matrix
