@@ -882,7 +882,9 @@ static int step_variant_choice(long tiles_per_layer, int sms) {
     if (forced < 0 || forced >= kStepVariants) forced = -1;
   }
   if (forced >= 0) return forced;
-  return tiles_per_layer >= 64L * sms ? 2 : 1;
+  // end of round 2 (role-specialised build): 8 x 2 also wins for very short layers (config 2, 27.7 tiles per SM: 6.93 vs 7.03 us
+  // sustained, 6.20 vs 6.40 burst); 12 x 2 keeps the middle (n = 4096: 10.15 vs 10.6 us)
+  return (tiles_per_layer >= 64L * sms || tiles_per_layer < 36L * sms) ? 2 : 1;
 }
 
 template <int D>
