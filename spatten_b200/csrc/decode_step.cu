@@ -90,13 +90,6 @@ __device__ __forceinline__ int nth_set_bit64(unsigned long long m, int n) {
   return 32 + __fns(static_cast<unsigned>(m >> 32), 0, n - cl + 1);
 }
 
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* ptr, int sys) {
-  unsigned v;
-  if (sys) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
-  else asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
-  return v;
-}
-
 __device__ __forceinline__ unsigned ld_relaxed(const unsigned* ptr, int sys) {
   unsigned v;
   if (sys) asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
@@ -225,9 +218,9 @@ __global__ void __launch_bounds__((WARPS + 2) * 32, 1) decode_step_kernel(const 
   const unsigned epoch = *reinterpret_cast<volatile const unsigned*>(p.ctrl);
   const unsigned flag_target = (epoch + 1u) * p.rows;
 
-  // wait until every producer's flag of `layer` has reached this step's target: relaxed polls, then ONE acquire load per
-  // flag by the lane that polled it, and a warp barrier that extends the ordering to the other lanes.  (A full
-  // fence.acq_rel.sys here costs ~2.6 us: 32 of them in the final wait of a head-sharded step were 83 us per step.)
+  // wait until every producer's flag of `layer` has reached this step's target: relaxed polls, then one acquire fence
+  // (`acquire` = false leaves the fence to the caller: a fence.acq_rel.sys costs ~2.6 us, and 32 of them in the final wait
+  // of a head-sharded step were 83 us per step)
   auto wait_layer = [&](int layer, bool acquire = true) {
     if (lane < p.wait_n) {
       const unsigned* f = p.wait_flags + static_cast<int64_t>(layer) * p.wait_n + lane;
@@ -236,10 +229,12 @@ __global__ void __launch_bounds__((WARPS + 2) * 32, 1) decode_step_kernel(const 
         if (clock64() - tw > 4000000000ll) { atomicExch(p.ctrl + 2, 1u); break; }   // ~2 s: never wedge the GPU
         __nanosleep(20);
       }
-      if (acquire && p.sys_scope) (void)ld_acquire(f, 1);
     }
     __syncwarp();
-    if (acquire && !p.sys_scope) asm volatile("fence.acq_rel.gpu;" ::: "memory");   // cheap at GPU scope
+    if (acquire) {
+      if (p.sys_scope) asm volatile("fence.acq_rel.sys;" ::: "memory");
+      else asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    }
   };
   auto seg_part = [&](unsigned seq) { return segbuf + (seq % NB) * kSegBufFloats; };
   auto seg_ml = [&](unsigned seq) { return reinterpret_cast<float2*>(seg_part(seq) + WARPS * D); };
