@@ -9,19 +9,23 @@
 // Why a second kernel.  At BASELINE config 2 one layer is 32 MiB = 5.2 us of HBM time; a per-layer launch pays
 // launch + first-byte latency + merge tail (about 5 us) every layer and cannot overlap them
 // with the next launch because one CTA owns the SM's whole shared memory.  Here one CTA per SM stays resident for
-// the whole step and the K/V stream never stops:
-//   * work list of a layer = (live row, 16-token tile) pairs in row-major order; it is cut into W equal contiguous
-//     ranges (W = warps in the grid), rotated by one warp per layer so the 3-vs-4-tile remainder evens out;
-//   * every warp owns a 3-stage ring of 16-token K+V tiles fed by 1-D bulk copies (cp.async.bulk -> mbarrier
-//     complete_tx).  The ISSUE cursor runs three tiles ahead of the CONSUME cursor and simply walks on into the next
-//     layer's range, so layer l+1's rows are landing in shared memory while layer l is merged;
-//   * a range may cover pieces of several rows ("segments").  A finished segment is reduce-scattered across the
-//     warp's 4 key groups (12 shuffles), written as one fp32 partial, and a per-(layer, row) ticket elects the last
-//     warp of the row, which merges the row's partials, stores the output row and bumps the layer's flag;
-//   * SPATTEN_STEP_CHAIN: the query of layer l+1 is read only after layer l's flag says every row is stored (the
+// the whole step and the K/V stream never stops.  Warps are role-specialised:
+//   * COMPUTE warps (8 or 12 per CTA) only stream.  The work list of a layer = (live row, 16-token tile) pairs in
+//     row-major order; it is cut into equal contiguous CTA ranges (rotated by one CTA per layer), and inside a CTA warp w
+//     takes range positions w, w + WARPS, ...  Every warp owns a ring of 16-token K+V tiles fed by 1-D bulk copies
+//     (cp.async.bulk -> mbarrier complete_tx); the ISSUE cursor runs STAGES tiles ahead of the CONSUME cursor and simply
+//     walks on into the next layer's range, so layer l+1's rows are landing in shared memory while layer l is merged.
+//     A range may cover pieces of several rows ("segments"); a finished segment is reduce-scattered across the warp's 4
+//     key groups (12 shuffles) into one of the CTA's shared-memory segment buffers.
+//   * the QUERY warp rotates the query of every segment into shared memory ahead of the compute warps.
+//     SPATTEN_STEP_CHAIN: the query of layer l+1 is read only after layer l's flag says every row is stored (the
 //     decoder's dependency); only the query load and the arithmetic wait, the K/V prefetch does not.
-//   * head sharding: the merged row is stored into every peer GPU's gather buffer by the whole warp (8-byte
-//     vectors) and lanes 0..N-1 each release one peer's per-layer flag -- no grid-wide counter, no serial loop.
+//   * the MERGE warp combines the warp partials of a segment, writes one CTA partial, and a per-(layer, row) ticket
+//     elects the last CTA of the row, whose merge warp merges the row's partials, stores the output row, adds the
+//     importance terms and bumps the layer's flag.  No global round trip of the merge path runs on a streaming warp.
+//   * head sharding: the merged row goes into this rank's slot of the LOCAL gather buffer; the merge warp of one
+//     designated CTA per layer copies the finished layer to every peer over NVLink and releases one system-scope flag
+//     per peer; the launch ends when every peer's flags of every layer have arrived (one acquire fence for all).
 #include <math_constants.h>
 
 #include <algorithm>

@@ -105,3 +105,25 @@ def test_cache_buffer_ownership_cpu():
     assert CacheBuffer.of(buf[:, :, :21]) is None          # a caller's own view of the same storage
     assert CacheBuffer.of(v21[:, :, :10]) is None and CacheBuffer.of(v21.clone()) is None
     assert CacheBuffer.of(None) is None
+
+
+def test_prefill_and_quant_argument_validation_without_gpu():
+    """Error codes of the entry points added in round 2 are decided before any CUDA call."""
+    from spatten_b200 import _lib
+    lib = _lib.load()
+    a = _lib.PrefillArgs()
+    assert lib.spatten_prefill_attn(C.byref(a), None) == -1 and b"struct_size" in lib.spatten_last_error()
+    a.struct_size = C.sizeof(a)
+    a.batch, a.num_heads, a.num_kv_heads, a.head_dim, a.q_len, a.kv_len, a.rope_len = 1, 4, 4, 64, 16, 16, 16
+    assert lib.spatten_prefill_attn(C.byref(a), None) == -2            # head_dim unsupported
+    a.head_dim, a.kv_len = 128, 8
+    assert lib.spatten_prefill_attn(C.byref(a), None) == -1            # kv_len < q_len
+    # scratch for the fused path: flag word + one 32 KiB image per (128-row tile) of Q, K and V
+    assert lib.spatten_prefill_scratch_bytes(1, 32, 32, 8192, 8192) == 1024 + (32 * 64 + 2 * 32 * 64) * 32768
+    assert lib.spatten_prefill_scratch_bytes(2, 8, 2, 129, 300) == 1024 + (2 * 8 * 2 + 2 * 2 * 2 * 3) * 32768
+    q = _lib.QuantDecodeArgs()
+    assert lib.spatten_decode_attn_quant(C.byref(q), None) == -1
+    q.struct_size = C.sizeof(q)
+    q.batch, q.num_heads, q.num_kv_heads, q.head_dim, q.kv_len, q.rope_len, q.v_bits = 1, 4, 4, 128, 16, 16, 5
+    assert lib.spatten_decode_attn_quant(C.byref(q), None) == -1 and b"v_bits" in lib.spatten_last_error()
+    assert lib.spatten_decode_quant_workspace_bytes(1, 32, 128) >= 8192 * (128 + 2) * 4 + 8192 * 4   # partials + tickets
