@@ -169,15 +169,16 @@ int spatten_decode_attn_host(const SpattenDecodeArgs* args, const void* q_host, 
  *                       one).  K/V prefetch of layer l+1 still overlaps.  With n_peers > 0 the chain runs over the
  *                       fused exchange instead: layer l+1 waits until all n_peers ranks have delivered layer l.
  *
- * Split-KV partials go through a workspace and per-(layer, row) tickets; the last warp of a row merges it.
+ * Split-KV partials go through a workspace and per-(layer, row) tickets; the merge warp of a row's last CTA merges it.
  * Outputs: layers[l].out (or, n_peers > 0, every peer's gather buffer), layers[l].logits, optional importance /
  * head_importance as in spatten_decode_attn.  head_mask is per layer: u8 [num_layers, num_heads] (<= 64 heads);
  * pruned heads cost no KV traffic and no work slot, their output rows are zeroed, and the appended K/V row is
  * still written (by the first live head of the kv group, or by the zeroing warp when the whole group is pruned).
  * ---------------------------------------------------------------------------------------------- */
 #define SPATTEN_STEP_CHAIN 1u
-/* Use the work split of the head-sharded build (the one with a communication warp) even without peers, so that a local
- * launch sums in exactly the order a sharded launch does -- lets a caller check the fused exchange bit for bit. */
+/* Historical: an earlier head-sharded build split the work differently from the local one, and this flag made a local
+ * launch sum in the sharded order so that the fused exchange could be checked bit for bit.  Both now share one work split
+ * (the flag is accepted and has no effect). */
 #define SPATTEN_STEP_SHARDED_LAYOUT 2u
 
 typedef struct SpattenStepLayer {   /* one per layer, array in DEVICE memory */
