@@ -123,3 +123,23 @@ def test_single_multiply_reproduces_the_fp16_logit_division():
     r_up = np.nextafter(r0, np.float32(1.0), dtype=np.float32)
     assert ((h.astype(np.float32) * r_up).astype(np.float16).view(np.uint16) == ref.view(np.uint16)).all()
     assert ((h.astype(np.float32) * r0).astype(np.float16).view(np.uint16) != ref.view(np.uint16)).sum() == 52
+
+
+def test_quant_plane_layout_chunks_hold_rope_partners():
+    """The int4 plane row of a 128-dim token (spatten_kv_quantize, oracle.quantize_kv_planes): 16-byte chunk kq carries the
+    MSB nibbles of dims [16kq, 16kq+16) followed by their RoPE partners [64+16kq, 64+16kq+16), 8 dims per little-endian u32
+    in the nibble order [d0,d2,d4,d6,d1,d3,d5,d7] -- the layout one lane of the tensor-core kernel fetches with one load."""
+    import numpy as np
+    x = torch.zeros(1, 128, dtype=torch.float16)
+    x[0] = torch.arange(128, dtype=torch.float16) - 64.0            # distinct codes: q = round(x / scale), scale = 64 / 127
+    msb, lsb, sc = O.quantize_kv_planes(x)
+    codes = O.dequant_ints(msb, lsb)[0].numpy()                     # int8 codes in dim order
+    assert (np.diff(codes) > 0).all()                               # round trip through pack / unpack keeps the dim order
+    u = (codes + 128).astype(np.int64)
+    words = msb[0].numpy().view("<u4")                              # 16 words of 8 nibbles
+    for kq in range(4):
+        for j, base in enumerate((16 * kq, 16 * kq + 8, 64 + 16 * kq, 64 + 16 * kq + 8)):
+            w = int(words[4 * kq + j])
+            nib = [(w >> (4 * p)) & 15 for p in range(8)]
+            dims = [base + d for d in (0, 2, 4, 6, 1, 3, 5, 7)]
+            assert nib == [int(u[d]) >> 4 for d in dims], (kq, j)
